@@ -1,0 +1,233 @@
+"""Pins the CPU oracle against the reference's own known-answer vectors (CPU only).
+
+Every case in tests/golden/*.json cites the reference #[test] / sqlness file it was ported from.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.helpers import (check_expected, farr, fnum, load_sqlness, load_unit, pack_series, promql_series,
+                           udf_case_inputs)
+
+UNIT = load_unit()
+SQL = load_sqlness()
+
+
+@pytest.mark.parametrize("case", UNIT["range_udf"], ids=lambda c: c["name"])
+def test_range_udf_golden(case):
+    ts, val, ranges = udf_case_inputs(case, UNIT)
+    out, valid = orc.range_udf(case["fn"], ts, val, ranges, eval_ts=case.get("eval_ts"),
+                               range_length=case.get("range_length", 0), param0=case.get("param0", 0.0),
+                               param1=case.get("param1", 0.0))
+    check_expected(out, valid, case["expected"], case["tol"], case["name"])
+    # nulls leave 0.0 in the raw buffer like an Arrow builder (extrapolate_rate.rs:497-523 asserts it)
+    assert all(out[i] == 0.0 for i, e in enumerate(case["expected"]) if e is None)
+
+
+@pytest.mark.parametrize("case", [c for c in UNIT["range_udf"] if c["fn"] in ("rate", "increase")],
+                         ids=lambda c: c["name"])
+def test_rate_rescan_equals_sliding_on_goldens(case):
+    ts, val, ranges = udf_case_inputs(case, UNIT)
+    a, va = orc.range_udf(case["fn"], ts, val, ranges, case["eval_ts"], case["range_length"])
+    b, vb = orc.range_udf(case["fn"], ts, val, ranges, case["eval_ts"], case["range_length"], rescan=True)
+    assert (va == vb).all() and (a == b).all()
+
+
+def test_holt_winters_trends():
+    g = UNIT["holt_winters_trends"]
+    for spec, expected in g["cases"]:
+        v = promql_series(spec)
+        ts = np.arange(v.size, dtype=np.int64)
+        out, valid = orc.range_udf("holt_winters", ts, v, [[0, 801]], param0=0.01, param1=0.1)
+        assert valid[0] and abs(out[0] - expected) < 1e-4, (spec, out[0])
+
+
+def test_holt_winters_impl():
+    for c in UNIT["holt_winters_impl"]["cases"]:
+        r = orc.holt_winters(farr(c["values"]), fnum(c["sf"]), fnum(c["tf"]))
+        e = fnum(c["expected"])
+        assert (math.isnan(r) and math.isnan(e)) or r == e, c
+
+
+def test_quantile_impl():
+    for c in UNIT["quantile_impl"]["cases"]:
+        r = orc.quantile(farr(c["values"]), fnum(c["q"]))
+        e = fnum(c["expected"])
+        assert (math.isnan(r) and math.isnan(e)) or r == e, c
+
+
+def test_linear_regression():
+    for c in UNIT["linear_regression"]["cases"]:
+        n = len(c["val"])
+        s, i = orc.linear_regression(c["ts"][:n], farr(c["val"]), c["intercept_time"])
+        assert s == c["slope"] and i == c["intercept"], c["name"]
+    k = UNIT["linear_regression"]["kahan"]
+    s, c = orc.compensated_sum(k["inputs"])
+    assert s + c == k["expected_sum_plus_c"]
+
+
+def test_histogram_evaluate_row():
+    for c in UNIT["histogram_evaluate_row"]["cases"]:
+        v, err = orc.histogram_evaluate_row(c["q"], farr(c["bucket"]), farr(c["counters"]))
+        if c["expected"] == "err":
+            assert err
+            continue
+        assert not err
+        e = fnum(c["expected"])
+        if math.isnan(e):
+            assert math.isnan(v), c
+        elif "tol" in c:
+            assert abs(v - e) < c["tol"], c
+        else:
+            # the reference compares format!("{actual}") == format!("{expected}")
+            assert repr(v) == repr(e), (c, v)
+
+
+def test_range_manipulate():
+    g = UNIT["range_manipulate"]
+    for c in g["cases"]:
+        for definitional in (False, True):
+            off, ln, s2, e2 = orc.calculate_range(g["ts"], c["start"], c["end"], c["interval"], c["range"], definitional)
+            assert list(zip(off.tolist(), ln.tolist())) == [tuple(r) for r in c["ranges"]], c["name"]
+            assert list(range(s2, e2 + 1, c["interval"])) == c["eval_ts"], c["name"]
+    a = g["alignment"]
+    off, ln, s2, e2 = orc.calculate_range(a["ts"], a["start"], a["end"], a["interval"], a["range"])
+    assert s2 % a["interval"] == a["start"] % a["interval"]
+    assert len(off) == len(range(s2, e2 + 1, a["interval"]))
+
+
+def test_range_manipulate_cursor_overshoot_quirk():
+    """the literal cursor walk reports an empty window when its cursor overshoots
+    len, although samples lie inside (t-range, t]; the definitional variant finds them."""
+    ts = [0, 1, 2, 3, 4, 100, 149, 150]
+    off, ln, _, _ = orc.calculate_range(ts, 0, 150, 50, 10)
+    offd, lnd, _, _ = orc.calculate_range(ts, 0, 150, 50, 10, definitional=True)
+    assert list(zip(offd.tolist(), lnd.tolist()))[-1] == (6, 2)
+    assert list(zip(off.tolist(), ln.tolist()))[-1] == (0, 0)
+
+
+def test_instant_manipulate():
+    g = UNIT["instant_manipulate"]
+    for c in g["cases"]:
+        d = g["data_nan"] if c["nan"] else g["data"]
+        take, ots = orc.instant_manipulate(d["ts"], farr(d["val"]), c["start"], c["end"], c["interval"], c["lookback"])
+        assert ots.tolist() == c["out_ts"], c["name"]
+        if "out_val" in c:
+            assert farr(d["val"])[take.astype(np.int64)].tolist() == c["out_val"], c["name"]
+
+
+def test_normalize():
+    g = UNIT["normalize"]
+    for c in g["cases"]:
+        ts, val = orc.normalize(g["ts"], farr(g["val"]), c["offset"], c["filter_nan"])
+        assert ts.tolist() == c["out_ts"] and val.tolist() == c["out_val"], c["name"]
+    ts, val = orc.normalize([1, 2, 3], farr([1.0, "nan", 3.0]), 10, True)
+    assert ts.tolist() == [11, 13] and val.tolist() == [1.0, 3.0]
+    ts, val = orc.normalize([1, 2, 3], farr([1.0, "nan", 3.0]), 10, False)
+    assert ts.tolist() == [11, 12, 13]
+
+
+def test_series_divide():
+    offs = orc.series_divide([5, 5, 5, 7, 7, 9])
+    assert offs.tolist() == [0, 3, 5, 6]
+    assert orc.series_divide([]).tolist() == [0]
+    assert orc.series_divide([1]).tolist() == [0, 1]
+
+
+def _resolve_series(case):
+    return case["series"] if "series" in case else SQL["series_sets"][case["series_ref"]]
+
+
+@pytest.mark.parametrize("mode", ["flat", "faithful"])
+@pytest.mark.parametrize("case", SQL["range_cases"], ids=lambda c: c["name"])
+def test_sqlness_range_cases(case, mode):
+    names, ts, val, sid, offsets = pack_series(_resolve_series(case))
+    p = orc.make_params(case["fn"], case["start"], case["end"], case["interval"], case["range"],
+                        offset=case["offset"], filter_nan=True, param0=case.get("param0", 0.0))
+    out, valid = orc.range_query(p, ts, val, sid, offsets, mode=mode, threads=2)
+    T = orc.num_steps(case["start"], case["end"], case["interval"])
+    vb = orc.valid_to_bool(valid, T)
+    got = {}
+    for s, name in enumerate(names):
+        for k in range(T):
+            if vb[s, k]:
+                got[(name, case["start"] + k * case["interval"])] = out[s, k]
+    exp = {(n, t): fnum(v) for n, t, v in case["expected"]}
+    assert set(got) == set(exp), (case["name"], got)
+    for key, e in exp.items():
+        assert got[key] == e or (math.isnan(e) and math.isnan(got[key])), (case["name"], key, got[key], e)
+
+
+@pytest.mark.parametrize("case", SQL["instant_cases"], ids=lambda c: c["name"])
+def test_sqlness_instant_cases(case):
+    names, ts, val, sid, offsets = pack_series(case["series"])
+    out, valid = orc.instant_query(ts, val, offsets, case["start"], case["end"], case["interval"], case["lookback"],
+                                   case["offset"])
+    T = orc.num_steps(case["start"], case["end"], case["interval"])
+    vb = orc.valid_to_bool(valid, T)
+    got = {(names[s], case["start"] + k * case["interval"]): out[s, k]
+           for s in range(len(names)) for k in range(T) if vb[s, k]}
+    exp = {(n, t): fnum(v) for n, t, v in case["expected"]}
+    assert got == exp
+
+
+@pytest.mark.parametrize("case", SQL["histogram_cases"], ids=lambda c: c["name"])
+def test_sqlness_histogram_cases(case):
+    B = len(case["le"])
+    series = {f"b{b}": {"ts": case["bucket_ts"], "val": case["bucket_val"][b]} for b in range(B)}
+    names, ts, val, sid, offsets = pack_series(series)
+    p = orc.make_params(case["fn"], case["start"], case["end"], case["interval"], case["range"], offset=case["offset"])
+    rates, valid = orc.range_query(p, ts, val, sid, offsets)
+    T = orc.num_steps(case["start"], case["end"], case["interval"])
+    # `sum by (le, s)` with one series per group is the identity on values (planner.rs:334-452)
+    for q, expected in case["quantiles"]:
+        out, ov = orc.histogram_quantile(q, farr(case["le"]), rates, valid)
+        vb = orc.valid_to_bool(ov, T)
+        exp = expected if isinstance(expected, list) else [expected]
+        got = [out[0, k] for k in range(T) if vb[0, k]]
+        assert got == exp, (case["name"], q, got)
+
+
+def test_group_aggregate_matches_numpy():
+    rng = np.random.default_rng(7)
+    S, T, G = 64, 40, 5
+    vals = rng.normal(size=(S, T))
+    vb = rng.random((S, T)) > 0.3
+    valid = np.packbits(np.pad(vb, ((0, 0), (0, (-T) % 32))), axis=1, bitorder="little").view(np.uint32)
+    gid = rng.integers(0, G, S).astype(np.uint32)
+    s, c = orc.group_aggregate("sum", vals, valid, gid, G)
+    for g in range(G):
+        m = (gid == g)[:, None] & vb
+        assert (c[g] == m.sum(0)).all()
+        ref = np.zeros(T)
+        for si in range(S):  # sequential series order, like one DataFusion partition
+            if gid[si] == g:
+                ref += np.where(vb[si], vals[si], 0.0)
+        assert np.allclose(s[g], ref, rtol=0, atol=0) or (s[g] == ref).all()
+    a, _ = orc.group_aggregate("avg", vals, valid, gid, G)
+    assert np.allclose(a[c > 0], (s / np.maximum(c, 1))[c > 0])
+
+
+def test_synth_generator_matches_reference_bench_recurrence():
+    """closed-form generator == sequential recurrences of benches/bench_range_fn.rs:60-82 (scaled)."""
+    n = 300
+    for s in (0, 1, 5, 36, 37, 1000):
+        ts, val, sid = orc.synth_fill(s, 1, n, 1_700_000_000_000, 15000, 1000, 0, 0x5EED)
+        cur, ref = 0.0, []
+        for i in range(n):
+            cur += 1.0 + (i % 7) * 0.25
+            ref.append(cur * (1 + s % 13))
+        assert val.tolist() == ref
+        assert (np.diff(ts) > 0).all() and ((ts - 1_700_000_000_000 - np.arange(n) * 15000) < 1000).all()
+        ts, val, sid = orc.synth_fill(s, 1, n, 0, 15000, 0, 1, 0x5EED)
+        cur, ref = 0.0, []
+        for i in range(n):
+            if i > 0 and (i + s) % 37 == 0:
+                cur = 1.0
+            else:
+                cur += 1.0 + (i % 5) * 0.5
+            ref.append(cur * (1 + s % 13))
+        assert val.tolist() == ref
+        assert (ts == np.arange(n) * 15000).all()
