@@ -1,0 +1,765 @@
+// b2p_api.cu — C ABI of libb200promql.so (see include/b200promql.h).
+// Host-side runtime: context, stream, device scratch, kernel dispatch, slow-path completion.
+// There is NO CPU fallback anywhere in this file: every entry point either launches the CUDA
+// kernels or returns an error.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../../include/b200promql.h"
+#include "b2p_aggregate.cuh"
+#include "b2p_kernels.cuh"
+
+using namespace b2p;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(x)                                                                                   \
+  do {                                                                                          \
+    cudaError_t e__ = (x);                                                                      \
+    if (e__ != cudaSuccess) return fail(B2P_E_CUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return B2P_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(B2P_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    cap = want;
+    return B2P_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int kRing = 256;
+constexpr int kSlowCtas = 148;        // slow-path grid (4 warps per CTA)
+constexpr int kSlowWarps = kSlowCtas * 4;
+constexpr size_t kArenaDefaultRows = 1u << 20;
+
+}  // namespace
+
+struct b2p_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  Status* d_status = nullptr;
+  Status* h_status = nullptr;  // pinned mirror
+  DevBuf slow_list, arena_ts, arena_val, win_scratch;
+  size_t arena_rows = 0;
+  cudaEvent_t ev[4][2] = {};
+  bool ev_used[4] = {false, false, false, false};
+  long long launches = 0;
+  // last range call, kept so b2p_sync can re-run the slow path after growing the arena
+  RangeArgs last_args{};
+  int last_fn = -1;
+  bool pending_range = false;
+  long long last_slow = 0;
+  // host-API staging
+  DevBuf h_ts, h_val, h_sid, h_off, h_out, h_valid, h_aux0, h_aux1, h_aux2, h_aux3;
+  // group aggregate scratch
+  DevBuf g_keys_in, g_keys_out, g_vals_in, g_vals_out, g_goff, g_tmp;
+  // column reduce scratch
+  DevBuf c_psum, c_pcnt;
+  int fast_blocks_per_sm[B2P_FN__COUNT] = {};
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+void stage_begin(b2p_ctx* c, int stage) {
+  cudaEventRecord(c->ev[stage][0], c->stream);
+}
+void stage_end(b2p_ctx* c, int stage) {
+  cudaEventRecord(c->ev[stage][1], c->stream);
+  c->ev_used[stage] = true;
+}
+
+template <int FN>
+int launch_fast(b2p_ctx* c, const RangeArgs& a) {
+  constexpr size_t smem = (size_t)kWarpsPerCta * (kRing * 16 + kRing / 8);
+  auto kern = range_fast_kernel<FN, kRing>;
+  if (c->fast_blocks_per_sm[FN] == 0) {
+    int nb = 0;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarpsPerCta * 32, smem));
+    c->fast_blocks_per_sm[FN] = nb > 0 ? nb : 1;
+  }
+  const unsigned need = (a.n_series + kWarpsPerCta - 1) / kWarpsPerCta;
+  const unsigned cap = (unsigned)(c->num_sms * c->fast_blocks_per_sm[FN]);
+  const unsigned grid = need < cap ? need : cap;
+  if (grid == 0) return B2P_OK;
+  kern<<<grid, kWarpsPerCta * 32, smem, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+template <int FN>
+int launch_slow(b2p_ctx* c, const RangeArgs& a) {
+  range_slow_kernel<FN><<<kSlowCtas, 128, 0, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+template <int FN>
+int launch_udf(b2p_ctx* c, const int64_t* ts, const double* val, const int64_t* packed, const int64_t* eval_ts,
+               uint64_t n_win, int64_t range_length, double p0, double p1, double* out, uint8_t* valid) {
+  if (n_win == 0) return B2P_OK;
+  uint64_t blocks = (n_win + 127) / 128;
+  if (blocks > (uint64_t)c->num_sms * 32) blocks = (uint64_t)c->num_sms * 32;
+  range_udf_kernel<FN><<<(unsigned)blocks, 128, 0, c->stream>>>(ts, val, packed, eval_ts, n_win, range_length, p0, p1,
+                                                                 out, valid);
+  c->launches++;
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+#define B2P_FOR_EACH_FN(X) \
+  X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20)
+
+int dispatch_fast(b2p_ctx* c, int fn, const RangeArgs& a) {
+  switch (fn) {
+#define X(N) case N: return launch_fast<N>(c, a);
+    B2P_FOR_EACH_FN(X)
+#undef X
+  }
+  return fail(B2P_E_INVALID, "unknown fn_id %d", fn);
+}
+int dispatch_slow(b2p_ctx* c, int fn, const RangeArgs& a) {
+  switch (fn) {
+#define X(N) case N: return launch_slow<N>(c, a);
+    B2P_FOR_EACH_FN(X)
+#undef X
+  }
+  return fail(B2P_E_INVALID, "unknown fn_id %d", fn);
+}
+int dispatch_udf(b2p_ctx* c, int fn, const int64_t* ts, const double* val, const int64_t* packed,
+                 const int64_t* eval_ts, uint64_t n_win, int64_t range_length, double p0, double p1, double* out,
+                 uint8_t* valid) {
+  switch (fn) {
+#define X(N) case N: return launch_udf<N>(c, ts, val, packed, eval_ts, n_win, range_length, p0, p1, out, valid);
+    B2P_FOR_EACH_FN(X)
+#undef X
+  }
+  return fail(B2P_E_INVALID, "unknown fn_id %d", fn);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_grid(const b2p_range_params* p, uint32_t n_series, int64_t* T_out) {
+  if (!p) return fail(B2P_E_INVALID, "params is NULL");
+  if (p->interval <= 0) return fail(B2P_E_INVALID, "interval must be > 0 (got %lld)", (long long)p->interval);
+  if (p->range < 0) return fail(B2P_E_INVALID, "range must be >= 0");
+  if (p->fn_id < 0 || p->fn_id >= B2P_FN__COUNT) return fail(B2P_E_INVALID, "unknown fn_id %d", p->fn_id);
+  const int64_t T = b2p_num_steps(p->start, p->end, p->interval);
+  if (T > (int64_t)0x7fffff00) return fail(B2P_E_TOO_LARGE, "%lld eval steps: trim [start,end] to the data extent first", (long long)T);
+  if ((double)T * (double)n_series > 1.0e12) return fail(B2P_E_TOO_LARGE, "dense grid %lld x %u too large", (long long)T, n_series);
+  *T_out = T;
+  return B2P_OK;
+}
+
+int reset_status(b2p_ctx* c) {
+  CU(cudaMemsetAsync(c->d_status, 0, sizeof(Status), c->stream));
+  return B2P_OK;
+}
+
+int ensure_slow_scratch(b2p_ctx* c, uint32_t n_series, int64_t T) {
+  int rc;
+  if ((rc = c->slow_list.ensure((size_t)(n_series ? n_series : 1) * 4))) return rc;
+  if ((rc = c->win_scratch.ensure((size_t)kSlowWarps * (size_t)(T > 0 ? T : 1) * 8))) return rc;
+  if (c->arena_rows == 0) {
+    if ((rc = c->arena_ts.ensure(kArenaDefaultRows * 8))) return rc;
+    if ((rc = c->arena_val.ensure(kArenaDefaultRows * 8))) return rc;
+    c->arena_rows = kArenaDefaultRows;
+  }
+  return B2P_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b2p_last_error(void) { return g_err.c_str(); }
+const char* b2p_version(void) { return "b200promql 0.1 (sm_100a)"; }
+
+int64_t b2p_num_steps(int64_t start, int64_t end, int64_t interval) {
+  if (interval <= 0 || end < start) return 0;
+  return (end - start) / interval + 1;
+}
+
+b2p_ctx* b2p_create(int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    fail(B2P_E_CUDA, "no CUDA device: %s — libb200promql has no CPU fallback", cudaGetErrorString(e));
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) {
+    fail(B2P_E_INVALID, "device %d out of range (have %d)", device, ndev);
+    return nullptr;
+  }
+  b2p_ctx* c = new (std::nothrow) b2p_ctx();
+  if (!c) {
+    fail(B2P_E_NOMEM, "out of host memory");
+    return nullptr;
+  }
+  c->device = device;
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+  c->stream = c->own_stream;
+  ok = ok && cudaMalloc(&c->d_status, sizeof(Status)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&c->h_status, sizeof(Status)) == cudaSuccess;
+  for (int i = 0; ok && i < 4; ++i)
+    for (int j = 0; j < 2; ++j) ok = ok && cudaEventCreate(&c->ev[i][j]) == cudaSuccess;
+  if (!ok) {
+    fail(B2P_E_CUDA, "context creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    b2p_destroy(c);
+    return nullptr;
+  }
+  cudaMemset(c->d_status, 0, sizeof(Status));
+  return c;
+}
+
+void b2p_destroy(b2p_ctx* c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  for (DevBuf* b : {&c->slow_list, &c->arena_ts, &c->arena_val, &c->win_scratch, &c->h_ts, &c->h_val, &c->h_sid,
+                    &c->h_off, &c->h_out, &c->h_valid, &c->h_aux0, &c->h_aux1, &c->h_aux2, &c->h_aux3,
+                    &c->g_keys_in, &c->g_keys_out, &c->g_vals_in, &c->g_vals_out, &c->g_goff, &c->g_tmp, &c->c_psum,
+                    &c->c_pcnt})
+    b->release();
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (c->ev[i][j]) cudaEventDestroy(c->ev[i][j]);
+  if (c->d_status) cudaFree(c->d_status);
+  if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int b2p_set_stream(b2p_ctx* c, void* cuda_stream) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  return B2P_OK;
+}
+
+int64_t b2p_last_slow_series(b2p_ctx* c) { return c ? c->last_slow : -1; }
+int64_t b2p_launch_count(b2p_ctx* c) { return c ? c->launches : -1; }
+
+double b2p_last_kernel_ms(b2p_ctx* c, int stage) {
+  if (!c || stage < 0 || stage >= 4 || !c->ev_used[stage]) return -1.0;
+  DeviceGuard g(c->device);
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, c->ev[stage][0], c->ev[stage][1]) != cudaSuccess) {
+    cudaGetLastError();
+    return -1.0;
+  }
+  return (double)ms;
+}
+
+int b2p_sync(b2p_ctx* c) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  DeviceGuard g(c->device);
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(Status), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const Status st = *c->h_status;
+    c->last_slow = st.slow_count;
+    if (st.k0_errors & 1u) return fail(B2P_E_UNSORTED, "series-id column is not non-decreasing");
+    if (st.k0_errors & 2u) return fail(B2P_E_UNSORTED, "series id >= n_series");
+    if (!st.arena_overflow) {
+      c->pending_range = false;
+      return B2P_OK;
+    }
+    // slow-path arena too small: grow it and re-run only the slow kernel (the work list is intact)
+    if (!c->pending_range) return fail(B2P_E_NOMEM, "slow-path arena overflow with no pending call");
+    const size_t need = (size_t)st.arena_needed + 1024;
+    int rc;
+    if ((rc = c->arena_ts.ensure(need * 8))) return rc;
+    if ((rc = c->arena_val.ensure(need * 8))) return rc;
+    c->arena_rows = need;
+    c->last_args.arena_ts = c->arena_ts.as<int64_t>();
+    c->last_args.arena_val = c->arena_val.as<double>();
+    c->last_args.arena_cap = need;
+    Status patch = st;
+    patch.arena_overflow = 0;
+    patch.arena_used = 0;
+    patch.arena_needed = 0;
+    *c->h_status = patch;
+    CU(cudaMemcpyAsync(c->d_status, c->h_status, sizeof(Status), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if ((rc = dispatch_slow(c, c->last_fn, c->last_args))) return rc;
+  }
+  return fail(B2P_E_NOMEM, "slow-path arena could not be sized");
+}
+
+/* ---- device-pointer API ---------------------------------------------------------------------- */
+
+int b2p_series_offsets_dev(b2p_ctx* c, const uint32_t* sid, uint64_t n_rows, uint32_t n_series, uint64_t* offsets) {
+  if (!c || !offsets || (!sid && n_rows)) return fail(B2P_E_INVALID, "NULL argument");
+  if (!aligned16(sid)) return fail(B2P_E_INVALID, "sid must be 16-byte aligned");
+  DeviceGuard g(c->device);
+  uint64_t blocks = (n_rows / 4 + 255) / 256;
+  const uint64_t cap = (uint64_t)c->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  CU(cudaMemsetAsync(&c->d_status->k0_errors, 0, sizeof(uint32_t), c->stream));
+  stage_begin(c, 0);
+  series_offsets_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(sid, n_rows, n_series, offsets, c->d_status);
+  c->launches++;
+  stage_end(c, 0);
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val,
+                       const uint64_t* offsets, uint64_t n_rows, uint32_t n_series, double* out,
+                       uint32_t* valid_words) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  int64_t T = 0;
+  int rc = check_grid(p, n_series, &T);
+  if (rc) return rc;
+  if (n_series == 0 || T == 0) return B2P_OK;
+  if (!offsets || !out || !valid_words || ((!ts || !val) && n_rows)) return fail(B2P_E_INVALID, "NULL argument");
+  if (!aligned16(ts) || !aligned16(val)) return fail(B2P_E_INVALID, "ts/val must be 16-byte aligned");
+  DeviceGuard g(c->device);
+  if ((rc = ensure_slow_scratch(c, n_series, T))) return rc;
+  RangeArgs a{};
+  a.start = p->start; a.end = p->end; a.interval = p->interval; a.range = p->range; a.offset = p->offset;
+  a.p0 = p->param0; a.p1 = p->param1; a.filter_nan = p->filter_nan;
+  a.T = T; a.Tw = (uint32_t)((T + 31) / 32);
+  a.ts = ts; a.val = val; a.offsets = offsets; a.n_rows = n_rows; a.n_series = n_series;
+  a.out = out; a.valid = valid_words;
+  a.status = c->d_status; a.slow_list = c->slow_list.as<uint32_t>();
+  a.arena_ts = c->arena_ts.as<int64_t>(); a.arena_val = c->arena_val.as<double>(); a.arena_cap = c->arena_rows;
+  a.win_scratch = c->win_scratch.as<unsigned long long>();
+  // the status block also carries K0's verdict; only the slow-path fields are reset here
+  CU(cudaMemsetAsync(&c->d_status->slow_count, 0, 2 * sizeof(uint32_t), c->stream));
+  CU(cudaMemsetAsync(&c->d_status->arena_used, 0, 2 * sizeof(unsigned long long), c->stream));
+  stage_begin(c, 1);
+  rc = dispatch_fast(c, p->fn_id, a);
+  stage_end(c, 1);
+  if (rc) return rc;
+  stage_begin(c, 2);
+  rc = dispatch_slow(c, p->fn_id, a);
+  stage_end(c, 2);
+  if (rc) return rc;
+  c->last_args = a;
+  c->last_fn = p->fn_id;
+  c->pending_range = true;
+  return B2P_OK;
+}
+
+int b2p_range_udf_dev(b2p_ctx* c, int32_t fn_id, const int64_t* ts, const double* val, uint64_t n_rows,
+                      const int64_t* packed_ranges, const int64_t* eval_ts, uint64_t n_win, int64_t range_length,
+                      double param0, double param1, double* out, uint8_t* valid) {
+  (void)n_rows;
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (n_win == 0) return B2P_OK;
+  if (!packed_ranges || !out || !valid) return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  stage_begin(c, 1);
+  int rc = dispatch_udf(c, fn_id, ts, val, packed_ranges, eval_ts, n_win, range_length, param0, param1, out, valid);
+  stage_end(c, 1);
+  return rc;
+}
+
+int b2p_instant_select_dev(b2p_ctx* c, int64_t start, int64_t end, int64_t interval, int64_t lookback, int64_t offset,
+                           const int64_t* ts, const double* val, const uint64_t* offsets, uint64_t n_rows,
+                           uint32_t n_series, double* out, uint32_t* valid_words) {
+  (void)n_rows;
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  b2p_range_params p{};
+  p.start = start; p.end = end; p.interval = interval; p.range = lookback;
+  int64_t T = 0;
+  int rc = check_grid(&p, n_series, &T);
+  if (rc) return rc;
+  if (n_series == 0 || T == 0) return B2P_OK;
+  if (!offsets || !out || !valid_words) return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  InstantArgs a{};
+  a.start = start; a.end = end; a.interval = interval; a.lookback = lookback; a.offset = offset;
+  a.T = T; a.Tw = (uint32_t)((T + 31) / 32);
+  a.ts = ts; a.val = val; a.offsets = offsets; a.n_series = n_series; a.out = out; a.valid = valid_words;
+  unsigned need = (n_series + kWarpsPerCta - 1) / kWarpsPerCta;
+  unsigned cap = (unsigned)c->num_sms * 8;
+  stage_begin(c, 1);
+  instant_kernel<<<need < cap ? need : cap, kWarpsPerCta * 32, 0, c->stream>>>(a);
+  c->launches++;
+  stage_end(c, 1);
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+int b2p_group_aggregate_dev(b2p_ctx* c, int32_t agg, const double* vals, const uint32_t* valid_words,
+                            const uint32_t* gid, uint32_t n_series, uint32_t n_groups, uint64_t T, double* out_val,
+                            uint32_t* out_cnt) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (agg < 0 || agg > B2P_AGG_STDVAR) return fail(B2P_E_INVALID, "unknown aggregator %d", agg);
+  if (n_groups == 0 || T == 0) return B2P_OK;
+  if (!vals || !valid_words || !gid || !out_val || !out_cnt) return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  int rc;
+  const size_t ns = n_series ? n_series : 1;
+  if ((rc = c->g_vals_in.ensure(ns * 4))) return rc;
+  if ((rc = c->g_vals_out.ensure(ns * 4))) return rc;
+  if ((rc = c->g_keys_out.ensure(ns * 4))) return rc;
+  if ((rc = c->g_goff.ensure(((size_t)n_groups + 1) * 4))) return rc;
+  stage_begin(c, 3);
+  // group -> member series CSR: stable radix sort of (gid, series index)
+  iota_kernel<<<(unsigned)((ns + 255) / 256 < 1024 ? (ns + 255) / 256 : 1024), 256, 0, c->stream>>>(
+      c->g_vals_in.as<uint32_t>(), n_series);
+  c->launches++;
+  size_t tmp_bytes = 0;
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, gid, c->g_keys_out.as<uint32_t>(), c->g_vals_in.as<uint32_t>(),
+                                     c->g_vals_out.as<uint32_t>(), (int)n_series, 0, 32, c->stream));
+  if ((rc = c->g_tmp.ensure(tmp_bytes ? tmp_bytes : 16))) return rc;
+  if (n_series > 0)
+    CU(cub::DeviceRadixSort::SortPairs(c->g_tmp.p, tmp_bytes, gid, c->g_keys_out.as<uint32_t>(),
+                                       c->g_vals_in.as<uint32_t>(), c->g_vals_out.as<uint32_t>(), (int)n_series, 0, 32,
+                                       c->stream));
+  group_offsets_kernel<<<(n_groups + 1 + 255) / 256, 256, 0, c->stream>>>(c->g_keys_out.as<uint32_t>(), n_series,
+                                                                          n_groups, c->g_goff.as<uint32_t>());
+  c->launches++;
+  GroupArgs a{};
+  a.agg = agg; a.vals = vals; a.valid = valid_words; a.goff = c->g_goff.as<uint32_t>();
+  a.members = c->g_vals_out.as<uint32_t>(); a.n_groups = n_groups; a.T = T; a.Tw = (uint32_t)((T + 31) / 32);
+  a.out_val = out_val; a.out_cnt = out_cnt; a.accumulate = 0;
+  const uint64_t warps = (uint64_t)n_groups * ((T + 31) / 32);
+  uint64_t blocks = (warps + 7) / 8;
+  const uint64_t cap = (uint64_t)c->num_sms * 32;
+  if (blocks > cap) blocks = cap;
+  group_aggregate_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(a);
+  c->launches++;
+  stage_end(c, 3);
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+int b2p_range_group_sum_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val,
+                            const uint64_t* offsets, uint64_t n_rows, uint32_t n_series, const uint32_t* gid,
+                            uint32_t n_groups, double* out_sum, uint32_t* out_cnt) {
+  // Composition for now: range function into context scratch, then by-label partial SUM/COUNT.
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  int64_t T = 0;
+  int rc = check_grid(p, n_series, &T);
+  if (rc) return rc;
+  if (n_series == 0 || T == 0 || n_groups == 0) return B2P_OK;
+  DeviceGuard g(c->device);
+  const uint32_t Tw = (uint32_t)((T + 31) / 32);
+  if ((rc = c->h_aux0.ensure((size_t)n_series * (size_t)T * 8))) return rc;
+  if ((rc = c->h_aux1.ensure((size_t)n_series * Tw * 4))) return rc;
+  if ((rc = c->h_aux2.ensure((size_t)n_groups * (size_t)T * 8))) return rc;
+  if ((rc = c->h_aux3.ensure((size_t)n_groups * (size_t)T * 4))) return rc;
+  if ((rc = b2p_range_eval_dev(c, p, ts, val, offsets, n_rows, n_series, c->h_aux0.as<double>(),
+                               c->h_aux1.as<uint32_t>())))
+    return rc;
+  if ((rc = b2p_sync(c))) return rc;  // slow-path fix-ups must land before the aggregate reads
+  if ((rc = b2p_group_aggregate_dev(c, B2P_AGG_SUM, c->h_aux0.as<double>(), c->h_aux1.as<uint32_t>(), gid, n_series,
+                                    n_groups, (uint64_t)T, c->h_aux2.as<double>(), c->h_aux3.as<uint32_t>())))
+    return rc;
+  // out += partial
+  const uint64_t n = (uint64_t)n_groups * (uint64_t)T;
+  uint64_t blocks = (n + 255) / 256;
+  if (blocks > (uint64_t)c->num_sms * 16) blocks = (uint64_t)c->num_sms * 16;
+  accumulate_partials_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(out_sum, out_cnt, c->h_aux2.as<double>(), c->h_aux3.as<uint32_t>(), n);
+  c->launches++;
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+int b2p_group_finalize_dev(b2p_ctx* c, int32_t agg, double* val, const uint32_t* cnt, uint64_t n) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (n == 0) return B2P_OK;
+  DeviceGuard g(c->device);
+  uint64_t blocks = (n + 255) / 256;
+  if (blocks > (uint64_t)c->num_sms * 16) blocks = (uint64_t)c->num_sms * 16;
+  group_finalize_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(agg, val, cnt, n);
+  c->launches++;
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+int b2p_histogram_quantile_dev(b2p_ctx* c, double phi, const double* le, uint32_t n_buckets, const double* rates,
+                               const uint32_t* valid_words, uint32_t n_hist, uint64_t T, double* out,
+                               uint32_t* out_valid_words) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (n_hist == 0 || T == 0) return B2P_OK;
+  if (!le || !rates || !valid_words || !out || !out_valid_words || n_buckets == 0)
+    return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  HistArgs a{};
+  a.phi = phi; a.le = le; a.B = n_buckets; a.rates = rates; a.valid = valid_words; a.n_hist = n_hist; a.T = T;
+  a.Tw = (uint32_t)((T + 31) / 32); a.out = out; a.out_valid = out_valid_words;
+  const uint64_t warps = (uint64_t)n_hist * ((T + 31) / 32);
+  uint64_t blocks = (warps + 7) / 8;
+  const uint64_t cap = (uint64_t)c->num_sms * 32;
+  if (blocks > cap) blocks = cap;
+  stage_begin(c, 3);
+  histogram_quantile_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(a);
+  c->launches++;
+  stage_end(c, 3);
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+int b2p_column_reduce_dev(b2p_ctx* c, const double* const* cols, uint32_t n_cols, uint64_t n_rows, double* out_sum,
+                          uint64_t* out_cnt) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (n_cols == 0 || n_rows == 0) return B2P_OK;
+  if (!cols || !out_sum || !out_cnt) return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  unsigned bpc = (unsigned)((c->num_sms * 8 + n_cols - 1) / n_cols);
+  if (bpc < 1) bpc = 1;
+  const uint64_t max_useful = (n_rows + 511) / 512;
+  if (bpc > max_useful) bpc = (unsigned)max_useful;
+  int rc;
+  if ((rc = c->c_psum.ensure((size_t)n_cols * bpc * 8))) return rc;
+  if ((rc = c->c_pcnt.ensure((size_t)n_cols * bpc * 8))) return rc;
+  stage_begin(c, 3);
+  column_reduce_stage1<<<dim3(bpc, n_cols), 256, 0, c->stream>>>(cols, n_rows, c->c_psum.as<double>(),
+                                                                 c->c_pcnt.as<unsigned long long>());
+  column_reduce_stage2<<<n_cols, 32, 0, c->stream>>>(c->c_psum.as<double>(), c->c_pcnt.as<unsigned long long>(), bpc,
+                                                     out_sum, reinterpret_cast<unsigned long long*>(out_cnt));
+  c->launches += 2;
+  stage_end(c, 3);
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+int b2p_synth_fill_dev(b2p_ctx* c, uint64_t series_begin, uint64_t n_series, uint32_t n_samples, int64_t t0,
+                       int64_t scrape_ms, uint32_t jitter_ms, int32_t with_resets, uint64_t seed, int64_t* ts,
+                       double* val, uint32_t* sid) {
+  if (!c || !ts || !val) return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  const uint64_t total = n_series * (uint64_t)n_samples;
+  if (total == 0) return B2P_OK;
+  uint64_t blocks = (total + 255) / 256;
+  if (blocks > (uint64_t)c->num_sms * 32) blocks = (uint64_t)c->num_sms * 32;
+  synth_fill_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(series_begin, n_series, n_samples, t0, scrape_ms,
+                                                             jitter_ms, with_resets, seed, ts, val, sid);
+  c->launches++;
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+/* ---- host-pointer API ------------------------------------------------------------------------ */
+
+int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val, const uint32_t* sid,
+                   const uint64_t* offsets_host, uint64_t n_rows, uint32_t n_series, double* out,
+                   uint32_t* valid_words, int64_t* out_ts) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  int64_t T = 0;
+  int rc = check_grid(p, n_series, &T);
+  if (rc) return rc;
+  if (out_ts)
+    for (int64_t k = 0; k < T; ++k) out_ts[k] = p->start + k * p->interval;
+  if (n_series == 0 || T == 0) return B2P_OK;
+  if (!sid && !offsets_host) return fail(B2P_E_INVALID, "need sid or offsets_host");
+  if (!out || !valid_words || ((!ts || !val) && n_rows)) return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  const uint32_t Tw = (uint32_t)((T + 31) / 32);
+  const size_t rows = n_rows ? n_rows : 1;
+  if ((rc = c->h_ts.ensure(rows * 8 + 16))) return rc;
+  if ((rc = c->h_val.ensure(rows * 8 + 16))) return rc;
+  if ((rc = c->h_off.ensure(((size_t)n_series + 1) * 8))) return rc;
+  if ((rc = c->h_out.ensure((size_t)n_series * (size_t)T * 8))) return rc;
+  if ((rc = c->h_valid.ensure((size_t)n_series * Tw * 4))) return rc;
+  if ((rc = reset_status(c))) return rc;
+  CU(cudaMemcpyAsync(c->h_ts.p, ts, n_rows * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->h_val.p, val, n_rows * 8, cudaMemcpyHostToDevice, c->stream));
+  if (offsets_host) {
+    CU(cudaMemcpyAsync(c->h_off.p, offsets_host, ((size_t)n_series + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    if ((rc = c->h_sid.ensure(rows * 4 + 16))) return rc;
+    CU(cudaMemcpyAsync(c->h_sid.p, sid, n_rows * 4, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = b2p_series_offsets_dev(c, c->h_sid.as<uint32_t>(), n_rows, n_series, c->h_off.as<uint64_t>()))) return rc;
+  }
+  if ((rc = b2p_range_eval_dev(c, p, c->h_ts.as<int64_t>(), c->h_val.as<double>(), c->h_off.as<uint64_t>(), n_rows,
+                               n_series, c->h_out.as<double>(), c->h_valid.as<uint32_t>())))
+    return rc;
+  if ((rc = b2p_sync(c))) return rc;
+  CU(cudaMemcpyAsync(out, c->h_out.p, (size_t)n_series * (size_t)T * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(valid_words, c->h_valid.p, (size_t)n_series * Tw * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B2P_OK;
+}
+
+int b2p_range_udf(b2p_ctx* c, int32_t fn_id, const int64_t* ts, const double* val, uint64_t n_rows,
+                  const int64_t* packed_ranges, const int64_t* eval_ts, uint64_t n_win, int64_t range_length,
+                  double param0, double param1, double* out, uint8_t* valid) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (n_win == 0) return B2P_OK;
+  if (!packed_ranges || !out || !valid) return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  int rc;
+  const size_t rows = n_rows ? n_rows : 1;
+  if ((rc = c->h_ts.ensure(rows * 8 + 16))) return rc;
+  if ((rc = c->h_val.ensure(rows * 8 + 16))) return rc;
+  if ((rc = c->h_aux0.ensure(n_win * 8))) return rc;
+  if ((rc = c->h_aux1.ensure(n_win * 8))) return rc;
+  if ((rc = c->h_out.ensure(n_win * 8))) return rc;
+  if ((rc = c->h_valid.ensure(n_win))) return rc;
+  if (n_rows) {
+    CU(cudaMemcpyAsync(c->h_ts.p, ts, n_rows * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->h_val.p, val, n_rows * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaMemcpyAsync(c->h_aux0.p, packed_ranges, n_win * 8, cudaMemcpyHostToDevice, c->stream));
+  if (eval_ts) CU(cudaMemcpyAsync(c->h_aux1.p, eval_ts, n_win * 8, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = b2p_range_udf_dev(c, fn_id, c->h_ts.as<int64_t>(), c->h_val.as<double>(), n_rows, c->h_aux0.as<int64_t>(),
+                              eval_ts ? c->h_aux1.as<int64_t>() : nullptr, n_win, range_length, param0, param1,
+                              c->h_out.as<double>(), c->h_valid.as<uint8_t>())))
+    return rc;
+  CU(cudaMemcpyAsync(out, c->h_out.p, n_win * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(valid, c->h_valid.p, n_win, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B2P_OK;
+}
+
+int b2p_instant_select(b2p_ctx* c, int64_t start, int64_t end, int64_t interval, int64_t lookback, int64_t offset,
+                       const int64_t* ts, const double* val, const uint32_t* sid, const uint64_t* offsets_host,
+                       uint64_t n_rows, uint32_t n_series, double* out, uint32_t* valid_words) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  b2p_range_params p{};
+  p.start = start; p.end = end; p.interval = interval; p.range = lookback;
+  int64_t T = 0;
+  int rc = check_grid(&p, n_series, &T);
+  if (rc) return rc;
+  if (n_series == 0 || T == 0) return B2P_OK;
+  if (!sid && !offsets_host) return fail(B2P_E_INVALID, "need sid or offsets_host");
+  DeviceGuard g(c->device);
+  const uint32_t Tw = (uint32_t)((T + 31) / 32);
+  const size_t rows = n_rows ? n_rows : 1;
+  if ((rc = c->h_ts.ensure(rows * 8 + 16))) return rc;
+  if ((rc = c->h_val.ensure(rows * 8 + 16))) return rc;
+  if ((rc = c->h_off.ensure(((size_t)n_series + 1) * 8))) return rc;
+  if ((rc = c->h_out.ensure((size_t)n_series * (size_t)T * 8))) return rc;
+  if ((rc = c->h_valid.ensure((size_t)n_series * Tw * 4))) return rc;
+  if ((rc = reset_status(c))) return rc;
+  CU(cudaMemcpyAsync(c->h_ts.p, ts, n_rows * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->h_val.p, val, n_rows * 8, cudaMemcpyHostToDevice, c->stream));
+  if (offsets_host) {
+    CU(cudaMemcpyAsync(c->h_off.p, offsets_host, ((size_t)n_series + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    if ((rc = c->h_sid.ensure(rows * 4 + 16))) return rc;
+    CU(cudaMemcpyAsync(c->h_sid.p, sid, n_rows * 4, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = b2p_series_offsets_dev(c, c->h_sid.as<uint32_t>(), n_rows, n_series, c->h_off.as<uint64_t>()))) return rc;
+  }
+  if ((rc = b2p_instant_select_dev(c, start, end, interval, lookback, offset, c->h_ts.as<int64_t>(),
+                                   c->h_val.as<double>(), c->h_off.as<uint64_t>(), n_rows, n_series,
+                                   c->h_out.as<double>(), c->h_valid.as<uint32_t>())))
+    return rc;
+  if ((rc = b2p_sync(c))) return rc;
+  CU(cudaMemcpyAsync(out, c->h_out.p, (size_t)n_series * (size_t)T * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(valid_words, c->h_valid.p, (size_t)n_series * Tw * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B2P_OK;
+}
+
+int b2p_group_aggregate(b2p_ctx* c, int32_t agg, const double* vals, const uint32_t* valid_words, const uint32_t* gid,
+                        uint32_t n_series, uint32_t n_groups, uint64_t T, double* out_val, uint32_t* out_cnt) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (n_groups == 0 || T == 0) return B2P_OK;
+  DeviceGuard g(c->device);
+  int rc;
+  const uint32_t Tw = (uint32_t)((T + 31) / 32);
+  const size_t ns = n_series ? n_series : 1;
+  if ((rc = c->h_aux0.ensure(ns * T * 8))) return rc;
+  if ((rc = c->h_aux1.ensure(ns * Tw * 4))) return rc;
+  if ((rc = c->h_aux2.ensure(ns * 4))) return rc;
+  if ((rc = c->h_out.ensure((size_t)n_groups * T * 8))) return rc;
+  if ((rc = c->h_valid.ensure((size_t)n_groups * T * 4))) return rc;
+  CU(cudaMemcpyAsync(c->h_aux0.p, vals, (size_t)n_series * T * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->h_aux1.p, valid_words, (size_t)n_series * Tw * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->h_aux2.p, gid, (size_t)n_series * 4, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = b2p_group_aggregate_dev(c, agg, c->h_aux0.as<double>(), c->h_aux1.as<uint32_t>(), c->h_aux2.as<uint32_t>(),
+                                    n_series, n_groups, T, c->h_out.as<double>(), c->h_valid.as<uint32_t>())))
+    return rc;
+  CU(cudaMemcpyAsync(out_val, c->h_out.p, (size_t)n_groups * T * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(out_cnt, c->h_valid.p, (size_t)n_groups * T * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B2P_OK;
+}
+
+int b2p_histogram_quantile(b2p_ctx* c, double phi, const double* le, uint32_t n_buckets, const double* rates,
+                           const uint32_t* valid_words, uint32_t n_hist, uint64_t T, double* out,
+                           uint32_t* out_valid_words) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (n_hist == 0 || T == 0) return B2P_OK;
+  DeviceGuard g(c->device);
+  int rc;
+  const uint32_t Tw = (uint32_t)((T + 31) / 32);
+  const size_t ns = (size_t)n_hist * n_buckets;
+  if ((rc = c->h_aux0.ensure(ns * T * 8))) return rc;
+  if ((rc = c->h_aux1.ensure(ns * Tw * 4))) return rc;
+  if ((rc = c->h_aux2.ensure((size_t)n_buckets * 8))) return rc;
+  if ((rc = c->h_out.ensure((size_t)n_hist * T * 8))) return rc;
+  if ((rc = c->h_valid.ensure((size_t)n_hist * Tw * 4))) return rc;
+  CU(cudaMemcpyAsync(c->h_aux0.p, rates, ns * T * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->h_aux1.p, valid_words, ns * Tw * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->h_aux2.p, le, (size_t)n_buckets * 8, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = b2p_histogram_quantile_dev(c, phi, c->h_aux2.as<double>(), n_buckets, c->h_aux0.as<double>(),
+                                       c->h_aux1.as<uint32_t>(), n_hist, T, c->h_out.as<double>(),
+                                       c->h_valid.as<uint32_t>())))
+    return rc;
+  CU(cudaMemcpyAsync(out, c->h_out.p, (size_t)n_hist * T * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(out_valid_words, c->h_valid.p, (size_t)n_hist * Tw * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B2P_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,620 @@
+// b2p_kernels.cuh — CUDA kernels (sm_100a) of the PromQL range-query path.
+//
+//  K0 series_offsets_kernel   SeriesDivide: series boundaries from the sorted u32 id column
+//  K2 range_fast_kernel<FN>   SeriesNormalize + RangeManipulate + prom_* UDF + IS NOT NULL, fused:
+//                             one warp per series, samples streamed with 128-bit coalesced loads
+//                             into a per-warp shared-memory ring, lanes own consecutive eval steps
+//     range_slow_kernel<FN>   exact fallback (literal calculate_range cursor walk) for the rare
+//                             series the fast kernel defers (ring overflow, cursor-overshoot quirk)
+//     range_udf_kernel<FN>    one prom_* UDF call over an explicit RangeArray (thread per window)
+//  K4 instant_kernel          InstantManipulate
+//
+// HBM traffic per input sample: K0 reads 4 B (sid); K2 reads 16 B (ts, val) and writes 8 B + 1 bit
+// per (series, step).  Window re-use (each sample is in ~range/interval windows) is served from the
+// shared-memory ring, never from HBM.
+#pragma once
+#include <cstdint>
+
+#include "b2p_window.cuh"
+
+namespace b2p {
+
+constexpr int kWarpsPerCta = 8;
+
+// Device-side status block, reset before every range/instant call.
+struct Status {
+  uint32_t slow_count;      // series deferred to the slow path          (reset per range call)
+  uint32_t arena_overflow;  // slow-path arena too small                 (reset per range call)
+  uint32_t k0_errors;       // bit0: sid not sorted, bit1: sid >= n_series (reset per K0 call)
+  uint32_t pad;
+  unsigned long long arena_used;    // rows claimed in the slow-path arena
+  unsigned long long arena_needed;  // rows that would have been needed
+};
+
+struct RangeArgs {
+  // query
+  int64_t start, end, interval, range, offset;
+  double p0, p1;
+  int32_t filter_nan;
+  int64_t T;    // global eval steps
+  uint32_t Tw;  // validity words per series
+  // input
+  const int64_t* ts;
+  const double* val;
+  const uint64_t* offsets;
+  uint64_t n_rows;
+  uint32_t n_series;
+  // output
+  double* out;
+  uint32_t* valid;
+  // slow path plumbing
+  Status* status;
+  uint32_t* slow_list;
+  int64_t* arena_ts;
+  double* arena_val;
+  unsigned long long arena_cap;
+  unsigned long long* win_scratch;  // [slow warps][T] packed (off | len<<32)
+};
+
+__device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b) {  // b > 0
+  int64_t q = a / b;
+  return (a % b < 0) ? q - 1 : q;
+}
+__device__ __forceinline__ int64_t rem_euclid(int64_t a, int64_t b) {
+  int64_t r = a % b;
+  return r < 0 ? r + b : r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0: series offsets.  offsets[s] = first row with sid >= s (lower bound), offsets[n_series] = n.
+// Replaces find_first_diff_row's row-by-row tag compare (series_divide.rs:622-670); ids must be
+// non-decreasing (the reference requires the same ordering, series_divide.rs:410-440).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) series_offsets_kernel(const uint32_t* __restrict__ sid, uint64_t n_rows,
+                                                             uint32_t n_series, uint64_t* __restrict__ offsets,
+                                                             Status* status) {
+  const uint64_t n4 = (n_rows + 3) / 4;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r0 = q * 4;
+    uint32_t v[4];
+    if (r0 + 3 < n_rows) {
+      uint4 x = __ldcs(reinterpret_cast<const uint4*>(sid + r0));
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = (r0 + i < n_rows) ? sid[r0 + i] : 0u;
+    }
+    uint32_t prev = (r0 == 0) ? 0u : sid[r0 - 1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint64_t r = r0 + i;
+      if (r >= n_rows) break;
+      const uint32_t cur = v[i];
+      if (cur >= n_series) {
+        atomicOr(&status->k0_errors, 2u);
+      } else if (r == 0) {
+        for (uint32_t s = 0; s <= cur; ++s) offsets[s] = 0;
+      } else if (cur != prev) {
+        if (cur < prev)
+          atomicOr(&status->k0_errors, 1u);
+        else
+          for (uint32_t s = prev + 1; s <= cur; ++s) offsets[s] = r;
+      }
+      if (r == n_rows - 1 && cur < n_series)
+        for (uint32_t s = cur + 1; s <= n_series; ++s) offsets[s] = n_rows;
+      prev = cur;
+    }
+  }
+  if (n_rows == 0 && blockIdx.x == 0)
+    for (uint32_t s = threadIdx.x; s <= n_series; s += blockDim.x) offsets[s] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 fast path.
+// ---------------------------------------------------------------------------------------------
+struct BlockRegs {  // one lane's share (2 rows) of a 64-row block
+  int64_t t0, t1;
+  double v0, v1;
+  bool in0, in1;
+};
+
+__device__ __forceinline__ BlockRegs load_block(const RangeArgs& a, uint64_t blk, uint64_t row0, uint64_t row1,
+                                                int lane) {
+  BlockRegs b;
+  const uint64_t r = blk + 2u * (uint64_t)lane;
+  b.in0 = (r >= row0) && (r < row1);
+  b.in1 = (r + 1 >= row0) && (r + 1 < row1);
+  b.t0 = b.t1 = 0;
+  b.v0 = b.v1 = 0.0;
+  if (b.in0 || b.in1) {
+    if (r + 1 < a.n_rows) {  // both rows inside the allocation: one 128-bit load per column
+      longlong2 tt = __ldcs(reinterpret_cast<const longlong2*>(a.ts + r));
+      double2 vv = __ldcs(reinterpret_cast<const double2*>(a.val + r));
+      b.t0 = tt.x; b.t1 = tt.y;
+      b.v0 = vv.x; b.v1 = vv.y;
+    } else {  // very last row of an odd-length column
+      b.t0 = a.ts[r];
+      b.v0 = a.val[r];
+    }
+  }
+  return b;
+}
+
+template <int FN, int RING>
+struct SeriesState {
+  // warp-uniform
+  uint32_t j_cnt;    // samples inserted so far (ordinal space after NaN filtering)
+  uint32_t base_lo;  // lower bound of every future window start
+  int32_t base_hi;   // lower bound (index) of every future window end
+  int32_t stride_lo, stride_hi;
+  int64_t k_next;    // next global step to evaluate
+  int64_t kf;        // first step the reference evaluates for this series (T = none)
+  uint32_t vword;    // validity bits of the current aligned 32-step group
+  uint32_t lrs;      // calculate_range's last_range_start (for the overshoot check)
+  uint32_t max_c0;   // max cursor start (range_start_index + start_delta) feeding a non-empty window
+  uint32_t carry_c0; // c0 of the last step of the previous group
+  bool any_nonempty;
+};
+
+// Evaluate global steps [k_a, k_b) (inside one aligned group of 32); lane = k & 31.
+template <int FN, int RING>
+__device__ __forceinline__ void process_steps(const RangeArgs& a, SeriesState<FN, RING>& st, const RingAcc<RING>& acc,
+                                              double* out_s, uint32_t* vw_s, int64_t k_a, int64_t k_b, int64_t kl,
+                                              int lane) {
+  const int64_t k = (k_a & ~31ll) + lane;
+  const bool active = (k >= k_a) && (k < k_b);
+  const int idx = (int)(k - k_a);
+  const int n_act = (int)(k_b - k_a);
+  const int64_t te = a.start + k * a.interval;
+  const int64_t tlo = te - a.range;
+  int32_t hi = st.base_hi;
+  uint32_t lo = st.base_lo;
+  if (active && st.j_cnt > 0) {
+    // window end: last ordinal with ts <= te.  Guess from the previous group's stride, then walk.
+    int32_t g = st.base_hi + (idx + 1) * st.stride_hi;
+    const int32_t top = (int32_t)st.j_cnt - 1;
+    g = g > top ? top : g;
+    while (g < top && acc.t((uint32_t)(g + 1)) <= te) ++g;
+    while (g > st.base_hi && acc.t((uint32_t)g) > te) --g;
+    hi = g;
+    // window start: first ordinal with ts > te - range, in [base_lo, hi+1]
+    uint32_t q = st.base_lo + (uint32_t)((idx + 1) * st.stride_lo);
+    const uint32_t qtop = (uint32_t)(hi + 1);
+    q = q > qtop ? qtop : q;
+    while (q > st.base_lo && acc.t(q - 1) > tlo) --q;
+    while (q < qtop && acc.t(q) <= tlo) ++q;
+    lo = q;
+  }
+  const uint32_t l = (active && (int32_t)lo <= hi) ? (uint32_t)(hi + 1 - (int32_t)lo) : 0u;
+  const bool in_grid = active && (k >= st.kf) && (k <= kl);
+  double r = 0.0;
+  bool ok = false;
+  if (in_grid) ok = eval_window<FN>(acc, lo, l, te, a.range, a.p0, a.p1, r);
+  if (!ok) r = 0.0;
+
+  // --- calculate_range cursor-overshoot watch -----------------------------------
+  // The reference's cursor for step k+1 starts at c0 = range_start_index_k + start_delta_k; when
+  // c0 >= m (#samples) it reports an EMPTY window even if samples are inside.  Record the largest c0
+  // whose following step has a non-empty true window; compared with m at the end of the series.
+  const bool nonempty = in_grid && l > 0;
+  const uint32_t ne_mask = __ballot_sync(0xffffffffu, nonempty);
+  {
+    const uint32_t before = ne_mask & ((1u << lane) - 1u);
+    const int src = before ? (31 - __clz(before)) : 0;
+    const uint32_t lo_src = __shfl_sync(0xffffffffu, lo, src);
+    const uint32_t my_lrs = before ? lo_src : st.lrs;
+    const bool brk = (hi + 1 < (int32_t)st.j_cnt);  // a sample newer than the window end exists
+    const uint32_t rsi = (brk && lo > 0) ? lo - 1 : lo;
+    const uint32_t c0 = nonempty ? (rsi + (lo - my_lrs)) : 0u;  // empty window => start_delta = 0 < m
+    const int last = (int)((k_b - 1) & 31);
+    const bool next_ne = (ne_mask >> ((lane + 1) & 31)) & 1u;
+    uint32_t watch = (lane < last && next_ne) ? c0 : 0u;
+    if (idx == 0 && nonempty) watch = max(watch, st.carry_c0);  // previous group's last step precedes me
+    st.max_c0 = max(st.max_c0, __reduce_max_sync(0xffffffffu, watch));
+    st.carry_c0 = __shfl_sync(0xffffffffu, c0, last);
+    if (ne_mask) {
+      st.lrs = __shfl_sync(0xffffffffu, lo, 31 - __clz(ne_mask));
+      st.any_nonempty = true;
+    }
+  }
+
+  // --- outputs -------------------------------------------------------------------------------------
+  if (active) out_s[k] = r;
+  st.vword |= __ballot_sync(0xffffffffu, ok);
+  if (((k_b & 31) == 0 || k_b == a.T)) {
+    if (lane == 0) vw_s[(k_b - 1) >> 5] = st.vword;
+    st.vword = 0;
+  }
+
+  // --- advance the warp-uniform search bases ------------------------------------------------------
+  if (st.j_cnt > 0) {
+    const int last = (int)((k_b - 1) & 31);
+    const int32_t nhi = __shfl_sync(0xffffffffu, hi, last);
+    const uint32_t nlo = __shfl_sync(0xffffffffu, lo, last);
+    st.stride_hi = (nhi - st.base_hi + n_act / 2) / n_act;
+    st.stride_lo = (int32_t)(nlo - st.base_lo + (uint32_t)n_act / 2) / n_act;
+    st.base_hi = nhi;
+    st.base_lo = nlo;
+  }
+}
+
+template <int FN, int RING>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) range_fast_kernel(const RangeArgs a) {
+  constexpr int FW = RING / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t* rts = reinterpret_cast<int64_t*>(smem_raw) + warp * RING;
+  double* rval = reinterpret_cast<double*>(smem_raw + (size_t)kWarpsPerCta * RING * 8) + warp * RING;
+  uint32_t* rfl = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kWarpsPerCta * RING * 16) + warp * FW;
+  const RingAcc<RING> acc{rts, rval, rfl};
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t total_warps = gridDim.x * kWarpsPerCta;
+
+  for (uint32_t s = blockIdx.x * kWarpsPerCta + warp; s < a.n_series; s += total_warps) {
+    const uint64_t row0 = a.offsets[s], row1 = a.offsets[s + 1];
+    double* out_s = a.out + (size_t)s * (size_t)a.T;
+    uint32_t* vw_s = a.valid + (size_t)s * a.Tw;
+    SeriesState<FN, RING> st;
+    st.j_cnt = 0; st.base_lo = 0; st.base_hi = -1; st.stride_lo = 1; st.stride_hi = 1;
+    st.k_next = 0; st.kf = a.T; st.vword = 0; st.lrs = 0; st.max_c0 = 0; st.carry_c0 = 0; st.any_nonempty = false;
+    bool defer = false;
+
+    uint64_t blk = row0 & ~1ull;  // 16-byte aligned pair boundary
+    BlockRegs nxt = load_block(a, blk, row0, row1, lane);
+    while (blk < row1 && !defer) {
+      const BlockRegs cur = nxt;
+      const uint64_t blk_next = blk + 64;
+      if (blk_next < row1) nxt = load_block(a, blk_next, row0, row1, lane);
+
+      // ---- SeriesNormalize: drop NaN rows, bias timestamps; append survivors to the ring ----------
+      const bool k0 = cur.in0 && !(a.filter_nan && isnan(cur.v0));
+      const bool k1 = cur.in1 && !(a.filter_nan && isnan(cur.v1));
+      const uint32_t b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
+      const uint32_t j0 = st.j_cnt;
+      const uint32_t pos0 = j0 + __popc(b0 & lt) + __popc(b1 & lt);
+      const uint32_t pos1 = pos0 + (k0 ? 1u : 0u);
+      if (k0) { rts[pos0 & (RING - 1)] = cur.t0 + a.offset; rval[pos0 & (RING - 1)] = cur.v0; }
+      if (k1) { rts[pos1 & (RING - 1)] = cur.t1 + a.offset; rval[pos1 & (RING - 1)] = cur.v1; }
+      st.j_cnt = j0 + __popc(b0) + __popc(b1);
+      __syncwarp();
+      if (st.j_cnt != j0) {
+        if constexpr (FnTraits<FN>::kUsesFlags) {
+          // reset/change bits of the new ordinals, one aligned 32-bit word per pass
+          for (uint32_t wb = j0 & ~31u; wb < st.j_cnt; wb += 32) {
+            const uint32_t j = wb + lane;
+            bool f = false;
+            if (j >= 1 && j < st.j_cnt) f = flag_pred<FN>(acc.v(j), acc.v(j - 1));
+            const uint32_t word = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) rfl[(wb >> 5) & (FW - 1)] = word;
+          }
+          __syncwarp();
+        }
+        if (j0 == 0) {  // first surviving sample: RangeManipulate start trimming (range_manipulate.rs:714-725)
+          const int64_t first_ts = acc.t(0);
+          const int64_t rem = rem_euclid(first_ts - a.start, a.interval);
+          const int64_t first_aligned = rem == 0 ? first_ts : first_ts + (a.interval - rem);
+          const int64_t s2 = a.start > first_aligned ? a.start : first_aligned;
+          const int64_t kf = (s2 - a.start) / a.interval;
+          st.kf = kf < a.T ? kf : a.T;
+        }
+        // steps whose window can no longer change and that the end-trim cannot remove
+        const int64_t ts_cur = acc.t(st.j_cnt - 1);
+        int64_t k_fin = floor_div(ts_cur - a.start, a.interval);
+        k_fin = k_fin < 0 ? 0 : (k_fin > a.T ? a.T : k_fin);
+        while (st.k_next < k_fin) {
+          if (st.j_cnt - st.base_lo > (uint32_t)(RING - 32)) { defer = true; break; }
+          int64_t g_end = (st.k_next | 31ll) + 1; if (g_end > k_fin) g_end = k_fin;
+          process_steps<FN, RING>(a, st, acc, out_s, vw_s, st.k_next, g_end, a.T - 1, lane);
+          st.k_next = g_end;
+        }
+      }
+      // ---- ring pressure: drop samples no future window can reach, then make room for 64 more ------
+      if (!defer && blk_next < row1 && st.j_cnt + 64u - st.base_lo > (uint32_t)(RING - 32)) {
+        const int64_t tlo_next = a.start + st.k_next * a.interval - a.range;
+        while (st.base_lo < st.j_cnt) {
+          const uint32_t j = st.base_lo + lane;
+          const bool dead = (j < st.j_cnt) && (acc.t(j) <= tlo_next);
+          const uint32_t m = __ballot_sync(0xffffffffu, dead);
+          const uint32_t adv = (m == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~m) - 1);
+          st.base_lo += adv;
+          if (adv < 32u) break;
+        }
+        if ((int32_t)st.base_lo - 1 > st.base_hi) st.base_hi = (int32_t)st.base_lo - 1;
+        if (st.j_cnt + 64u - st.base_lo > (uint32_t)(RING - 32)) defer = true;
+      }
+      blk = blk_next;
+    }
+
+    if (!defer) {
+      // ---- end of stream: RangeManipulate end trimming (range_manipulate.rs:722-728) --------------
+      int64_t kl = -1;
+      if (st.j_cnt > 0) {
+        const int64_t last_ts = acc.t(st.j_cnt - 1);
+        const int64_t last_aligned = ((last_ts + a.range) / a.interval) * a.interval;
+        const int64_t e2 = a.end < last_aligned ? a.end : last_aligned;
+        const int64_t s2 = a.start + st.kf * a.interval;
+        if (st.kf < a.T && e2 >= s2) kl = floor_div(e2 - a.start, a.interval);
+      }
+      while (st.k_next < a.T) {
+        if (st.j_cnt - st.base_lo > (uint32_t)(RING - 32)) { defer = true; break; }
+        int64_t g_end = (st.k_next | 31ll) + 1; if (g_end > a.T) g_end = a.T;
+        process_steps<FN, RING>(a, st, acc, out_s, vw_s, st.k_next, g_end, kl, lane);
+        st.k_next = g_end;
+      }
+      // cursor-overshoot quirk possible -> exact slow path decides
+      if (!defer && st.j_cnt > 0 && st.max_c0 >= st.j_cnt) defer = true;
+      // "ignore this if all ranges are empty" (range_manipulate.rs:641-643): absent_over_time is the only
+      // function that yields Some on an empty window, so it alone needs the series-level veto.
+      if (FN == B2P_FN_ABSENT_OVER_TIME && !defer && !st.any_nonempty) {
+        for (int64_t k = lane; k < a.T; k += 32) out_s[k] = 0.0;
+        for (uint32_t w = lane; w < a.Tw; w += 32) vw_s[w] = 0u;
+      }
+    }
+    if (defer && lane == 0) {
+      const uint32_t i = atomicAdd(&a.status->slow_count, 1u);
+      a.slow_list[i] = s;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 slow path: exact restatement on the device.  One warp per deferred series: compact the series
+// (SeriesNormalize) into a global arena, lane 0 runs the literal calculate_range cursor walk
+// (range_manipulate.rs:730-769) into a per-warp window list, then lanes evaluate the windows.
+// ---------------------------------------------------------------------------------------------
+template <int FN>
+__global__ void __launch_bounds__(128) range_slow_kernel(const RangeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t total_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_slow = a.status->slow_count;
+  unsigned long long* wins = a.win_scratch + (size_t)warp_global * (size_t)a.T;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (uint32_t w = warp_global; w < n_slow; w += total_warps) {
+    const uint32_t s = a.slow_list[w];
+    const uint64_t row0 = a.offsets[s], row1 = a.offsets[s + 1];
+    const uint64_t n = row1 - row0;
+    double* out_s = a.out + (size_t)s * (size_t)a.T;
+    uint32_t* vw_s = a.valid + (size_t)s * a.Tw;
+    for (int64_t k = lane; k < a.T; k += 32) out_s[k] = 0.0;
+    for (uint32_t q = lane; q < a.Tw; q += 32) vw_s[q] = 0u;
+    if (n == 0) continue;
+    unsigned long long base = 0;
+    if (lane == 0) {
+      base = atomicAdd(&a.status->arena_used, (unsigned long long)n);
+      atomicAdd(&a.status->arena_needed, (unsigned long long)n);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + n > a.arena_cap) {
+      if (lane == 0) atomicExch(&a.status->arena_overflow, 1u);
+      continue;
+    }
+    int64_t* cts = a.arena_ts + base;
+    double* cval = a.arena_val + base;
+    uint32_t m = 0;
+    for (uint64_t r = row0; r < row1; r += 32) {
+      const uint64_t rr = r + lane;
+      double v = 0.0;
+      int64_t t = 0;
+      bool keep = false;
+      if (rr < row1) {
+        v = a.val[rr];
+        t = a.ts[rr] + a.offset;
+        keep = !(a.filter_nan && isnan(v));
+      }
+      const uint32_t b = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const uint32_t p = m + __popc(b & lt);
+        cts[p] = t;
+        cval[p] = v;
+      }
+      m += __popc(b);
+    }
+    __syncwarp();
+    if (m == 0) continue;
+    // ---- literal calculate_range (lane 0) ------------------------------------------------------
+    int64_t s2 = 0, e2 = -1;
+    int64_t nwin = 0;
+    if (lane == 0) {
+      const int64_t first_ts = cts[0];
+      const int64_t rem = rem_euclid(first_ts - a.start, a.interval);
+      const int64_t first_aligned = rem == 0 ? first_ts : first_ts + (a.interval - rem);
+      const int64_t last_ts = cts[m - 1];
+      const int64_t last_aligned = ((last_ts + a.range) / a.interval) * a.interval;
+      s2 = a.start > first_aligned ? a.start : first_aligned;
+      e2 = a.end < last_aligned ? a.end : last_aligned;
+      uint32_t rsi = 0, last_range_start = 0, start_delta = 0;
+      for (int64_t curr = s2; curr <= e2; curr += a.interval) {
+        const int64_t start_ts = curr - a.range;
+        uint32_t range_start = m, range_end = 0;
+        uint32_t cursor = rsi + start_delta;
+        while (cursor < m && cts[cursor] > start_ts && cursor > 0) --cursor;
+        while (cursor < m) {
+          const int64_t t = cts[cursor];
+          if (range_start > cursor && t > start_ts) {
+            range_start = cursor;
+            rsi = range_start;
+          }
+          if (t <= curr) {
+            range_end = range_end > cursor ? range_end : cursor;
+          } else {
+            rsi = rsi > 0 ? rsi - 1 : 0;
+            break;
+          }
+          ++cursor;
+        }
+        const int64_t k = (curr - a.start) / a.interval;
+        unsigned long long packed = 0;
+        if (range_start > range_end) {
+          start_delta = 0;
+        } else {
+          packed = (unsigned long long)range_start | ((unsigned long long)(range_end + 1 - range_start) << 32);
+          start_delta = range_start - last_range_start;
+          last_range_start = range_start;
+        }
+        if (k >= 0 && k < a.T) wins[k] = packed;
+        ++nwin;
+      }
+    }
+    s2 = __shfl_sync(0xffffffffu, s2, 0);
+    e2 = __shfl_sync(0xffffffffu, e2, 0);
+    __syncwarp();
+    if (s2 > e2) continue;
+    const int64_t kf = (s2 - a.start) / a.interval;
+    const int64_t kl = floor_div(e2 - a.start, a.interval);
+    // all-empty veto (range_manipulate.rs:641-643)
+    bool any = false;
+    for (int64_t k = kf + lane; k <= kl; k += 32) any |= ((wins[k] >> 32) != 0ull);
+    if (!__any_sync(0xffffffffu, any)) continue;
+    const GlobalAcc acc{cts, cval};
+    for (int64_t kb = kf & ~31ll; kb <= kl; kb += 32) {
+      const int64_t k = kb + lane;
+      bool ok = false;
+      double r = 0.0;
+      if (k >= kf && k <= kl) {
+        const unsigned long long pk = wins[k];
+        ok = eval_window<FN>(acc, (uint32_t)(pk & 0xffffffffull), (uint32_t)(pk >> 32), a.start + k * a.interval,
+                             a.range, a.p0, a.p1, r);
+        if (ok) out_s[k] = r;
+      }
+      const uint32_t word = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) vw_s[kb >> 5] = word;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// UDF-level kernel: one prom_* ScalarUDF invocation over a RangeArray (range_array.rs:247-254:
+// key = offset | len<<32).  Thread per window.
+// ---------------------------------------------------------------------------------------------
+template <int FN>
+__global__ void __launch_bounds__(128) range_udf_kernel(const int64_t* __restrict__ ts, const double* __restrict__ val,
+                                                        const int64_t* __restrict__ packed,
+                                                        const int64_t* __restrict__ eval_ts, uint64_t n_win,
+                                                        int64_t range_length, double p0, double p1,
+                                                        double* __restrict__ out, uint8_t* __restrict__ valid) {
+  const GlobalAcc acc{ts, val};
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_win; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long pk = (unsigned long long)packed[i];
+    const int64_t te = eval_ts ? eval_ts[i] : 0;
+    double r = 0.0;
+    const bool ok =
+        eval_window<FN>(acc, (uint32_t)(pk & 0xffffffffull), (uint32_t)(pk >> 32), te, range_length, p0, p1, r);
+    out[i] = ok ? r : 0.0;
+    valid[i] = ok ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: InstantManipulate (instant_manipulate.rs:473-585).  Warp per series, lane per eval step:
+// newest sample with t - lookback < ts <= t; a NaN newest sample is a stale marker -> no row.
+// (lookback == 0 selects ts == t only, matching the reference's cursor walk.)
+// ---------------------------------------------------------------------------------------------
+struct InstantArgs {
+  int64_t start, end, interval, lookback, offset;
+  int64_t T;
+  uint32_t Tw;
+  const int64_t* ts;
+  const double* val;
+  const uint64_t* offsets;
+  uint32_t n_series;
+  double* out;
+  uint32_t* valid;
+};
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) instant_kernel(const InstantArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t total_warps = gridDim.x * kWarpsPerCta;
+  for (uint32_t s = blockIdx.x * kWarpsPerCta + warp; s < a.n_series; s += total_warps) {
+    const uint64_t row0 = a.offsets[s], row1 = a.offsets[s + 1];
+    const uint64_t n = row1 - row0;
+    double* out_s = a.out + (size_t)s * (size_t)a.T;
+    uint32_t* vw_s = a.valid + (size_t)s * a.Tw;
+    const int64_t* ts = a.ts + row0;
+    const double* val = a.val + row0;
+    int64_t k_lo = a.T, k_hi = -1;
+    if (n > 0) {
+      const int64_t first_ts = ts[0] + a.offset, last_ts = ts[n - 1] + a.offset;
+      const int64_t last_useful = a.lookback > 0 ? last_ts + a.lookback - 1 : last_ts;
+      const int64_t max_start = first_ts > a.start ? first_ts : a.start;
+      const int64_t min_end = last_useful < a.end ? last_useful : a.end;
+      const int64_t aligned_start = a.start + (max_start - a.start) / a.interval * a.interval;
+      const int64_t aligned_end = a.end - (a.end - min_end) / a.interval * a.interval;
+      if (aligned_start <= aligned_end) {
+        k_lo = (aligned_start - a.start) / a.interval;
+        k_hi = floor_div(aligned_end - a.start, a.interval);
+      }
+    }
+    for (int64_t kb = 0; kb < a.T; kb += 32) {
+      const int64_t k = kb + lane;
+      bool ok = false;
+      double r = 0.0;
+      if (k < a.T && k >= k_lo && k <= k_hi) {
+        const int64_t te = a.start + k * a.interval;
+        // last row with ts + offset <= te  (binary search over the series in global memory)
+        uint64_t lo = 0, hi = n;
+        while (lo < hi) {
+          const uint64_t mid = (lo + hi) >> 1;
+          if (ts[mid] + a.offset <= te) lo = mid + 1; else hi = mid;
+        }
+        if (lo > 0) {
+          const uint64_t j = lo - 1;
+          const int64_t t = ts[j] + a.offset;
+          const bool fresh = (a.lookback > 0) ? (t + a.lookback > te) : (t == te);
+          if (fresh) {
+            const double v = val[j];
+            if (!isnan(v)) { ok = true; r = v; }
+          }
+        }
+      }
+      if (k < a.T) out_s[k] = r;
+      const uint32_t word = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) vw_s[kb >> 5] = word;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic workload generator (bench/test utility).  Same integer/f64 arithmetic as
+// oracle/promql_oracle.c:orc_synth_fill.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256) synth_fill_kernel(uint64_t series_begin, uint64_t n_series, uint32_t n_samples,
+                                                         int64_t t0, int64_t scrape_ms, uint32_t jitter_ms,
+                                                         int with_resets, uint64_t seed, int64_t* __restrict__ ts,
+                                                         double* __restrict__ val, uint32_t* __restrict__ sid) {
+  const uint64_t total = n_series * (uint64_t)n_samples;
+  for (uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < total;
+       row += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t ls = row / n_samples;
+    const uint32_t i = (uint32_t)(row - ls * n_samples);
+    const uint64_t s = series_begin + ls;
+    const uint64_t h = mix64(seed ^ mix64(s * 0x100000001B3ull + i));
+    const int64_t jit = jitter_ms ? (int64_t)(h % jitter_ms) : 0;
+    ts[row] = t0 + (int64_t)i * scrape_ms + jit;
+    const double scale = (double)(1 + s % 13);
+    double v;
+    if (!with_resets) {
+      const uint32_t q = (i + 1) / 7, r = (i + 1) % 7;
+      v = (double)q * 12.25 + (double)r + 0.25 * (double)(r * (r - 1) / 2);
+      if (r == 0) v = (double)q * 12.25;
+    } else {
+      const uint32_t ph = (uint32_t)((i + s) % 37);
+      const bool has = (i >= ph) && (i - ph) > 0;
+      const uint32_t j0 = has ? (i - ph) + 1 : 0;
+      v = has ? 1.0 : 0.0;
+      for (uint32_t j = j0; j <= i; ++j) v += 1.0 + (double)(j % 5) * 0.5;
+    }
+    val[row] = v * scale;
+    if (sid) sid[row] = (uint32_t)ls;
+  }
+}
+
+}  // namespace b2p

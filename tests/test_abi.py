@@ -1,0 +1,64 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/b200promql.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from greptimedb_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "b200promql.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2p_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert _declared_symbols() == sorted(_lib.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.fail(f"{_lib.LIB_PATH} not built — run __graft_entry__.build()")
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _declared_symbols():
+        assert hasattr(L, name), f"symbol {name} missing from libb200promql.so"
+    _lib.load()  # signatures bind
+
+
+def test_pure_host_entry_points():
+    L = _lib.load()
+    assert L.b2p_num_steps(0, 310_000, 30_000) == 11
+    assert L.b2p_num_steps(10, 0, 5) == 0
+    assert b"sm_100a" in L.b2p_version()
+
+
+def test_params_struct_layout_matches_oracle():
+    from oracle import oracle as orc
+    assert ctypes.sizeof(_lib.RangeParams) == ctypes.sizeof(orc.Params) == 64
+    for (n1, _), (n2, _) in zip(_lib.RangeParams._fields_, orc.Params._fields_):
+        assert n1 == n2
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the product must fail loudly instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from greptimedb_b200 import B2PError, Context
+    with pytest.raises(B2PError) as ei:
+        Context(0)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "greptimedb_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle/" not in txt.replace("oracle/promql_oracle.c:orc_synth_fill", "") or f.endswith(".cuh"), f
+                assert "import oracle" not in txt and "from oracle" not in txt, f

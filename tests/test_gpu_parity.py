@@ -1,0 +1,369 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI,
+against (1) the reference's own golden vectors and (2) the CPU oracle on seeded inputs.
+
+Tolerances: resets / changes / count_over_time / validity bitmaps are compared BIT-EXACT.  Every
+other function is compared to the oracle's *rescan* restatement bit-exactly too (the library is
+compiled with -fmad=false and uses IEEE div/sqrt), and to the reference's *sliding* restatement
+within 1e-9 relative (the two reference code paths themselves differ in the last ulps,
+extrapolate_rate.rs:216-238).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.helpers import (check_expected, farr, fnum, load_sqlness, load_unit, pack_series, promql_series,
+                           udf_case_inputs)
+
+pytestmark = pytest.mark.gpu
+
+UNIT = load_unit()
+SQL = load_sqlness()
+REL = 1e-9
+
+ALL_FNS = ["rate", "increase", "delta", "irate", "idelta", "resets", "changes", "count_over_time", "sum_over_time",
+           "avg_over_time", "min_over_time", "max_over_time", "last_over_time", "present_over_time",
+           "absent_over_time", "stdvar_over_time", "stddev_over_time", "deriv", "predict_linear",
+           "quantile_over_time", "holt_winters"]
+FN_PARAMS = {"predict_linear": (600.0, 0.0), "quantile_over_time": (0.9, 0.0), "holt_winters": (0.3, 0.1)}
+BIT_EXACT = {"resets", "changes", "count_over_time", "present_over_time", "absent_over_time", "last_over_time",
+             "min_over_time", "max_over_time", "idelta"}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from greptimedb_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def assert_close(got, exp, gv, ev, what, bit_exact=False):
+    assert (gv == ev).all(), f"{what}: validity differs at {np.argwhere(gv != ev)[:5].tolist()}"
+    g, e = got[ev], exp[ev]
+    nan_g, nan_e = np.isnan(g), np.isnan(e)
+    assert (nan_g == nan_e).all(), f"{what}: NaN pattern differs"
+    g, e = g[~nan_e], e[~nan_e]
+    if bit_exact:
+        bad = g != e
+    else:
+        with np.errstate(invalid="ignore"):
+            bad = ~((g == e) | (np.abs(g - e) <= REL * np.maximum(np.abs(g), np.abs(e))))
+    assert not bad.any(), f"{what}: {int(bad.sum())} mismatches, first {g[bad][:3]} vs {e[bad][:3]}"
+    assert (got[~ev] == 0.0).all(), f"{what}: null slots must hold 0.0"
+
+
+# ---------------------------------------------------------------------------------------------------
+# 1. the reference's unit-test vectors, through the UDF-level entry point (b2p_range_udf)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", UNIT["range_udf"], ids=lambda c: c["name"])
+def test_udf_reference_goldens(ctx, case):
+    ts, val, ranges = udf_case_inputs(case, UNIT)
+    out, valid = ctx.range_udf(case["fn"], ts, val, ranges, eval_ts=case.get("eval_ts"),
+                               range_length=case.get("range_length", 0), param0=case.get("param0", 0.0),
+                               param1=case.get("param1", 0.0))
+    check_expected(out, valid, case["expected"], case["tol"], case["name"])
+    o_out, o_valid = orc.range_udf(case["fn"], ts, val, ranges, eval_ts=case.get("eval_ts"),
+                                   range_length=case.get("range_length", 0), param0=case.get("param0", 0.0),
+                                   param1=case.get("param1", 0.0), rescan=True)
+    assert (valid == o_valid).all() and (out.view(np.uint64) == o_out.view(np.uint64)).all(), "bit-exact vs oracle"
+
+
+def test_udf_holt_winters_trends(ctx):
+    for spec, expected in UNIT["holt_winters_trends"]["cases"]:
+        v = promql_series(spec)
+        ts = np.arange(v.size, dtype=np.int64)
+        out, valid = ctx.range_udf("holt_winters", ts, v, [[0, 801]], param0=0.01, param1=0.1)
+        assert valid[0] and abs(out[0] - expected) < 1e-4, (spec, out[0])
+
+
+def test_udf_quantile_and_edge_values(ctx):
+    for c in UNIT["quantile_impl"]["cases"]:
+        v = farr(c["values"])
+        ts = np.arange(max(v.size, 1), dtype=np.int64)
+        vv = v if v.size else np.zeros(1)
+        out, valid = ctx.range_udf("quantile_over_time", ts, vv, [[0, v.size]], param0=fnum(c["q"]))
+        e = fnum(c["expected"])
+        assert valid[0] and ((math.isnan(e) and math.isnan(out[0])) or out[0] == e), c
+    for c in UNIT["holt_winters_impl"]["cases"]:
+        v = farr(c["values"])
+        ts = np.arange(max(v.size, 1), dtype=np.int64)
+        vv = v if v.size else np.zeros(1)
+        out, valid = ctx.range_udf("holt_winters", ts, vv, [[0, v.size]], param0=fnum(c["sf"]), param1=fnum(c["tf"]))
+        e = fnum(c["expected"])
+        assert valid[0] and ((math.isnan(e) and math.isnan(out[0])) or out[0] == e), c
+
+
+# ---------------------------------------------------------------------------------------------------
+# 2. the reference's operator-level vectors through the fused sub-plan entry point (b2p_range_eval)
+# ---------------------------------------------------------------------------------------------------
+def test_range_manipulate_goldens_via_count(ctx):
+    """count_over_time exposes the window lengths RangeManipulate computed (range_manipulate.rs:995-1049)."""
+    g = UNIT["range_manipulate"]
+    ts = np.array(g["ts"], np.int64)
+    val = np.ones(ts.size)
+    for c in g["cases"]:
+        p = ctx_params("count_over_time", c)
+        out, valid, ets = ctx.range_eval(p, ts, val, offsets=[0, ts.size])
+        T = ets.size
+        vb = orc.valid_to_bool(valid, T)[0]
+        exp = {t: r[1] for t, r in zip(c["eval_ts"], c["ranges"]) if r[1] > 0}
+        got = {int(ets[k]): out[0, k] for k in range(T) if vb[k]}
+        assert got == {t: float(l) for t, l in exp.items()}, c["name"]
+        # last_over_time pins the window END, sum over ts-as-values pins the START
+        p2 = ctx_params("min_over_time", c)
+        out2, valid2, _ = ctx.range_eval(p2, ts, ts.astype(np.float64), offsets=[0, ts.size])
+        first = {int(ets[k]): out2[0, k] for k in range(T) if orc.valid_to_bool(valid2, T)[0][k]}
+        assert first == {t: float(ts[r[0]]) for t, r in zip(c["eval_ts"], c["ranges"]) if r[1] > 0}, c["name"]
+
+
+def ctx_params(fn, c, **kw):
+    from greptimedb_b200 import make_params
+    return make_params(fn, c["start"], c["end"], c["interval"], c["range"], offset=c.get("offset", 0),
+                       param0=c.get("param0", 0.0), **kw)
+
+
+@pytest.mark.parametrize("case", SQL["range_cases"], ids=lambda c: c["name"])
+def test_sqlness_range_cases(ctx, case):
+    series = case["series"] if "series" in case else SQL["series_sets"][case["series_ref"]]
+    names, ts, val, sid, offsets = pack_series(series)
+    p = ctx_params(case["fn"], case)
+    out, valid, ets = ctx.range_eval_n(p, ts, val, sid, None, len(names))
+    T = ets.size
+    vb = orc.valid_to_bool(valid, T)
+    got = {(names[s], int(ets[k])): out[s, k] for s in range(len(names)) for k in range(T) if vb[s, k]}
+    exp = {(n, t): fnum(v) for n, t, v in case["expected"]}
+    assert set(got) == set(exp), (case["name"], got)
+    for key, e in exp.items():
+        assert got[key] == e, (case["name"], key, got[key], e)
+
+
+@pytest.mark.parametrize("case", SQL["instant_cases"], ids=lambda c: c["name"])
+def test_sqlness_instant_cases(ctx, case):
+    names, ts, val, sid, offsets = pack_series(case["series"])
+    out, valid = ctx.instant_select(ts, val, case["start"], case["end"], case["interval"], case["lookback"],
+                                    case["offset"], offsets=offsets)
+    T = orc.num_steps(case["start"], case["end"], case["interval"])
+    vb = orc.valid_to_bool(valid, T)
+    got = {(names[s], case["start"] + k * case["interval"]): out[s, k]
+           for s in range(len(names)) for k in range(T) if vb[s, k]}
+    assert got == {(n, t): fnum(v) for n, t, v in case["expected"]}
+
+
+def test_instant_manipulate_goldens(ctx):
+    g = UNIT["instant_manipulate"]
+    for c in g["cases"]:
+        if c["name"] == "ultra_large_range":
+            continue  # 1.8e11-step grid: the host must trim to the data extent first (B2P_E_TOO_LARGE, below)
+        d = g["data_nan"] if c["nan"] else g["data"]
+        ts, val = np.array(d["ts"], np.int64), farr(d["val"])
+        out, valid = ctx.instant_select(ts, val, c["start"], c["end"], c["interval"], c["lookback"], 0,
+                                        offsets=[0, ts.size])
+        T = orc.num_steps(c["start"], c["end"], c["interval"])
+        vb = orc.valid_to_bool(valid, T)[0]
+        got_ts = [c["start"] + k * c["interval"] for k in range(T) if vb[k]]
+        assert got_ts == c["out_ts"], c["name"]
+        if "out_val" in c:
+            assert [out[0, k] for k in range(T) if vb[k]] == c["out_val"], c["name"]
+
+
+def test_too_large_grid_is_an_error_not_a_hang(ctx):
+    from greptimedb_b200 import B2PError
+    with pytest.raises(B2PError):
+        ctx.instant_select(np.array([0], np.int64), np.array([1.0]), -899999999999999, 900000000000000, 10000, 10000, 0,
+                           offsets=[0, 1])
+
+
+@pytest.mark.parametrize("case", SQL["histogram_cases"], ids=lambda c: c["name"])
+def test_sqlness_histogram_cases(ctx, case):
+    B = len(case["le"])
+    series = {f"b{b}": {"ts": case["bucket_ts"], "val": case["bucket_val"][b]} for b in range(B)}
+    names, ts, val, sid, offsets = pack_series(series)
+    p = ctx_params(case["fn"], case)
+    rates, valid, ets = ctx.range_eval_n(p, ts, val, sid, None, B)
+    # sum by (le, s): one series per group -> identity, but exercise the kernel anyway
+    gsum, gcnt = ctx.group_aggregate("sum", rates, valid, np.arange(B, dtype=np.uint32), B)
+    T = ets.size
+    Tw = (T + 31) // 32
+    gvalid = np.zeros((B, Tw), np.uint32)
+    for b in range(B):
+        for k in range(T):
+            if gcnt[b, k]:
+                gvalid[b, k >> 5] |= np.uint32(1 << (k & 31))
+    for q, expected in case["quantiles"]:
+        out, ov = ctx.histogram_quantile(q, farr(case["le"]), gsum, gvalid)
+        vb = orc.valid_to_bool(ov, T)
+        exp = expected if isinstance(expected, list) else [expected]
+        assert [out[0, k] for k in range(T) if vb[0, k]] == exp, (case["name"], q)
+
+
+def test_histogram_evaluate_row_goldens(ctx):
+    for c in UNIT["histogram_evaluate_row"]["cases"]:
+        le, counters = farr(c["bucket"]), farr(c["counters"])
+        B = le.size
+        rates = counters.reshape(B, 1)
+        valid = np.ones((B, 1), np.uint32)
+        out, ov = ctx.histogram_quantile(c["q"], le, rates, valid)
+        assert ov[0, 0] & 1
+        if c["expected"] == "err":
+            assert math.isnan(out[0, 0])  # Err -> unwrap_or(NaN), histogram_fold.rs:806
+            continue
+        e = fnum(c["expected"])
+        if math.isnan(e):
+            assert math.isnan(out[0, 0]), c
+        elif "tol" in c:
+            assert abs(out[0, 0] - e) < c["tol"], c
+        else:
+            assert repr(float(out[0, 0])) == repr(e), (c, out[0, 0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# 3. seeded parity against the oracle on synthetic series (every function)
+# ---------------------------------------------------------------------------------------------------
+def make_irregular(seed, n_series, with_nan=True):
+    rng = np.random.default_rng(seed)
+    ts_l, val_l, offs = [], [], [0]
+    for s in range(n_series):
+        kind = s % 6
+        n = int(rng.integers(0, 400)) if kind else int(rng.integers(0, 4))
+        if kind == 1:      # regular scrape
+            t = 1_000_000 + np.arange(n) * 15_000
+        elif kind == 2:    # jittered
+            t = 1_000_000 + np.arange(n) * 15_000 + rng.integers(0, 5_000, n)
+        elif kind == 3:    # gaps
+            t = 1_000_000 + np.cumsum(rng.choice([15_000, 15_000, 15_000, 400_000], n))
+        elif kind == 4:    # dense bursts + duplicates-free random increments
+            t = 900_000 + np.cumsum(rng.integers(1, 40_000, n))
+        else:
+            t = 1_200_000 + np.cumsum(rng.integers(1, 3_000, n))
+        v = np.cumsum(rng.random(n) * 10)
+        resets = rng.random(n) < 0.05
+        for i in np.flatnonzero(resets):
+            v[i:] -= v[i] * rng.random()
+        if kind == 4:
+            v = rng.normal(size=n) * 100
+        if with_nan and n:
+            v[rng.random(n) < 0.04] = np.nan
+        ts_l.append(t.astype(np.int64))
+        val_l.append(v.astype(np.float64))
+        offs.append(offs[-1] + n)
+    return (np.concatenate(ts_l) if ts_l else np.zeros(0, np.int64),
+            np.concatenate(val_l) if val_l else np.zeros(0), np.array(offs, np.uint64))
+
+
+QUERY_SHAPES = [
+    dict(start=1_000_000, end=4_000_000, interval=15_000, range=300_000, offset=0),
+    dict(start=999_001, end=7_000_000, interval=60_000, range=90_000, offset=0),       # unaligned start
+    dict(start=0, end=8_000_000, interval=7_000, range=20_000, offset=123_000),          # offset, short windows
+    dict(start=2_000_000, end=2_000_000, interval=1_000, range=600_000, offset=0),       # instant query
+    dict(start=1_000_000, end=9_000_000, interval=300_000, range=3_600_000, offset=0),   # long windows, sparse steps
+]
+
+
+@pytest.mark.parametrize("fn", ALL_FNS)
+def test_every_function_matches_oracle_on_irregular_series(ctx, fn):
+    from greptimedb_b200 import make_params
+    ts, val, offsets = make_irregular(1234, 96)
+    p0, p1 = FN_PARAMS.get(fn, (0.0, 0.0))
+    for qi, q in enumerate(QUERY_SHAPES):
+        p = make_params(fn, q["start"], q["end"], q["interval"], q["range"], offset=q["offset"], param0=p0, param1=p1)
+        out, valid, ets = ctx.range_eval(p, ts, val, offsets=offsets)
+        T = ets.size
+        op = orc.make_params(fn, q["start"], q["end"], q["interval"], q["range"], offset=q["offset"], param0=p0, param1=p1)
+        e_out, e_valid = orc.range_query(op, ts, val, None, offsets, mode="flat")
+        gv, ev = orc.valid_to_bool(valid, T), orc.valid_to_bool(e_valid, T)
+        assert_close(out, e_out, gv, ev, f"{fn} shape {qi}", bit_exact=fn in BIT_EXACT)
+
+
+def test_nan_filter_off_passes_nan_through(ctx):
+    from greptimedb_b200 import make_params
+    ts, val, offsets = make_irregular(77, 24)
+    for fn in ("last_over_time", "count_over_time", "changes"):
+        p = make_params(fn, 1_000_000, 4_000_000, 15_000, 300_000, filter_nan=False)
+        out, valid, ets = ctx.range_eval(p, ts, val, offsets=offsets)
+        op = orc.make_params(fn, 1_000_000, 4_000_000, 15_000, 300_000, filter_nan=False)
+        e_out, e_valid = orc.range_query(op, ts, val, None, offsets)
+        assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size), fn,
+                     bit_exact=True)
+
+
+def test_cursor_overshoot_quirk_is_reproduced(ctx):
+    """the reference reports an empty window when its cursor overshoots; so do we."""
+    from greptimedb_b200 import make_params
+    ts = np.array([0, 1, 2, 3, 4, 100, 149, 150], np.int64)
+    val = np.arange(8, dtype=np.float64)
+    p = make_params("count_over_time", 0, 150, 50, 10)
+    out, valid, ets = ctx.range_eval(p, ts, val, offsets=[0, 8])
+    vb = orc.valid_to_bool(valid, ets.size)[0]
+    assert ets.tolist() == [0, 50, 100, 150]
+    assert vb.tolist() == [True, False, True, False]          # the reference drops t=150 although {149,150} match
+    assert out[0].tolist() == [1.0, 0.0, 1.0, 0.0]
+    assert ctx.last_slow_series() == 1                         # decided by the exact slow path
+
+
+def test_long_windows_overflow_the_ring_and_still_match(ctx):
+    from greptimedb_b200 import make_params
+    n = 5000
+    ts = (np.arange(n) * 1000).astype(np.int64)
+    val = np.cumsum(np.ones(n))
+    val[::97] = 1.0
+    offsets = np.array([0, n, 2 * n], np.uint64)
+    ts2, val2 = np.concatenate([ts, ts]), np.concatenate([val, val * 2])
+    for fn in ("rate", "sum_over_time", "resets"):
+        p = make_params(fn, 0, n * 1000, 10_000, 2_000_000)     # 2000-sample windows >> 256-sample ring
+        out, valid, ets = ctx.range_eval(p, ts2, val2, offsets=offsets)
+        assert ctx.last_slow_series() == 2
+        op = orc.make_params(fn, 0, n * 1000, 10_000, 2_000_000)
+        e_out, e_valid = orc.range_query(op, ts2, val2, None, offsets)
+        assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size), fn,
+                     bit_exact=fn == "resets")
+
+
+def test_series_offsets_from_sid_and_unsorted_error(ctx):
+    from greptimedb_b200 import B2PError, make_params
+    ts, val, offsets = make_irregular(5, 40, with_nan=False)
+    sid = np.repeat(np.arange(40, dtype=np.uint32), np.diff(offsets).astype(np.int64))
+    p = make_params("rate", 1_000_000, 4_000_000, 15_000, 300_000)
+    a = ctx.range_eval_n(p, ts, val, sid, None, 40)
+    b = ctx.range_eval(p, ts, val, offsets=offsets)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    bad = sid.copy()
+    bad[[3, 4]] = bad[[4, 3]] if bad[3] != bad[4] else bad[[3, 4]]
+    bad[10:20] = bad[10:20][::-1]
+    if (np.diff(bad.astype(np.int64)) < 0).any():
+        with pytest.raises(B2PError) as ei:
+            ctx.range_eval_n(p, ts, val, bad, None, 40)
+        assert ei.value.code == -3
+
+
+def test_bench_shape_matches_oracle_both_variants(ctx):
+    """The BASELINE config-2 shape at a size the oracle finishes in seconds; jitter and reset variants."""
+    from greptimedb_b200 import make_params
+    S, N, T0 = 512, 1000, 1_700_000_000_000
+    for jitter, resets in ((0, 0), (1000, 0), (1000, 1)):
+        ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, jitter, resets, 0x5EED)
+        offsets = np.arange(S + 1, dtype=np.uint64) * N
+        p = make_params("rate", T0, T0 + 999 * 15_000, 15_000, 300_000)
+        out, valid, ets = ctx.range_eval_n(p, ts, val, sid, None, S)
+        assert ctx.last_slow_series() == 0
+        op = orc.make_params("rate", T0, T0 + 999 * 15_000, 15_000, 300_000)
+        e_out, e_valid = orc.range_query(op, ts, val, sid, offsets, mode="faithful", threads=4)
+        gv, ev = orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size)
+        assert_close(out, e_out, gv, ev, f"bench jitter={jitter} resets={resets}")
+        assert gv.sum() > 0.97 * S * 1000
+
+
+def test_group_aggregate_matches_oracle(ctx):
+    rng = np.random.default_rng(3)
+    S, T, G = 700, 77, 13
+    vals = rng.normal(size=(S, T))
+    vb = rng.random((S, T)) > 0.2
+    valid = np.packbits(np.pad(vb, ((0, 0), (0, (-T) % 32))), axis=1, bitorder="little").view(np.uint32)
+    vals = np.where(vb, vals, 0.0)
+    gid = rng.integers(0, G + 2, S).astype(np.uint32)   # ids >= G are dropped
+    for op in ("sum", "avg", "count", "min", "max", "stddev", "stdvar"):
+        g_out, g_cnt = ctx.group_aggregate(op, vals, valid, gid, G)
+        e_out, e_cnt = orc.group_aggregate(op, vals, valid, gid, G)
+        assert (g_cnt == e_cnt).all(), op
+        assert (g_out.view(np.uint64) == e_out.view(np.uint64)).all(), f"{op}: sequential series order is bit-exact"
