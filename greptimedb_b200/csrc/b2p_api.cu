@@ -97,7 +97,7 @@ struct b2p_ctx {
   DevBuf g_keys_in, g_keys_out, g_vals_in, g_vals_out, g_goff, g_tmp;
   // column reduce scratch
   DevBuf c_psum, c_pcnt;
-  int fast_blocks_per_sm[B2P_FN__COUNT] = {};
+  int fast_blocks_per_sm[B2P_FN__COUNT][2] = {};
 };
 
 namespace {
@@ -123,24 +123,36 @@ void stage_end(b2p_ctx* c, int stage) {
   c->ev_used[stage] = true;
 }
 
-template <int FN>
-int launch_fast(b2p_ctx* c, const RangeArgs& a) {
-  constexpr size_t smem = (size_t)kWarpsPerCta * (kRing * 16 + kRing / 8);
-  auto kern = range_fast_kernel<FN, kRing>;
-  if (c->fast_blocks_per_sm[FN] == 0) {
+template <int FN, bool TS32>
+int launch_fast_t(b2p_ctx* c, const RangeArgs& a) {
+  constexpr size_t smem = (size_t)kWarpsPerCta * (kRing * (8 + (TS32 ? 4 : 8)) + kRing / 8) + kRcpTable * 8;
+  auto kern = range_fast_kernel<FN, kRing, TS32>;
+  int& cached = c->fast_blocks_per_sm[FN][TS32 ? 1 : 0];
+  if (cached == 0) {
     int nb = 0;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarpsPerCta * 32, smem));
-    c->fast_blocks_per_sm[FN] = nb > 0 ? nb : 1;
+    cached = nb > 0 ? nb : 1;
   }
   const unsigned need = (a.n_series + kWarpsPerCta - 1) / kWarpsPerCta;
-  const unsigned cap = (unsigned)(c->num_sms * c->fast_blocks_per_sm[FN]);
+  const unsigned cap = (unsigned)(c->num_sms * cached);
   const unsigned grid = need < cap ? need : cap;
   if (grid == 0) return B2P_OK;
   kern<<<grid, kWarpsPerCta * 32, smem, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
   return B2P_OK;
+}
+
+// 32-bit relative timestamps when the whole query span (plus one lookback) fits 31 bits of ms.
+bool fits_ts32(const RangeArgs& a) {
+  const double span = (double)a.end - (double)a.start + (double)a.range;
+  return span >= 0 && span < 2147483000.0 && a.interval < 2147483000ll && a.range < 2147483000ll;
+}
+
+template <int FN>
+int launch_fast(b2p_ctx* c, const RangeArgs& a) {
+  return fits_ts32(a) ? launch_fast_t<FN, true>(c, a) : launch_fast_t<FN, false>(c, a);
 }
 
 template <int FN>
@@ -293,7 +305,13 @@ void b2p_destroy(b2p_ctx* c) {
 
 int b2p_set_stream(b2p_ctx* c, void* cuda_stream) {
   if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
-  c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);  // NULL == the legacy default stream
+  return B2P_OK;
+}
+
+int b2p_use_own_stream(b2p_ctx* c) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  c->stream = c->own_stream;
   return B2P_OK;
 }
 
@@ -382,6 +400,17 @@ int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts,
   a.start = p->start; a.end = p->end; a.interval = p->interval; a.range = p->range; a.offset = p->offset;
   a.p0 = p->param0; a.p1 = p->param1; a.filter_nan = p->filter_nan;
   a.T = T; a.Tw = (uint32_t)((T + 31) / 32);
+  a.tb = p->start - p->range;
+  a.rel_max = 0;
+  if (fits_ts32(a)) a.rel_max = (uint32_t)(p->range + (T - 1) * p->interval + 1);
+  {
+    // exact two-FMA division by range/1000 needs RN(1/b) and a significand that is not all ones
+    const double rs = (double)p->range / 1000.0;
+    uint64_t bits;
+    memcpy(&bits, &rs, 8);
+    const bool all_ones = (bits & 0x000fffffffffffffull) == 0x000fffffffffffffull;
+    a.rcp_rs = (p->range > 0 && !all_ones) ? 1.0 / rs : 0.0;
+  }
   a.ts = ts; a.val = val; a.offsets = offsets; a.n_rows = n_rows; a.n_series = n_series;
   a.out = out; a.valid = valid_words;
   a.status = c->d_status; a.slow_list = c->slow_list.as<uint32_t>();

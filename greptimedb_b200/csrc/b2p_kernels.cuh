@@ -38,6 +38,10 @@ struct RangeArgs {
   int32_t filter_nan;
   int64_t T;    // global eval steps
   uint32_t Tw;  // validity words per series
+  // derived (host): 32-bit time domain of the fast kernel and exact-division helper
+  int64_t tb;        // start - range: origin of the uint32 timestamps
+  uint32_t rel_max;  // range + (T-1)*interval + 1: clamp for samples after `end`
+  double rcp_rs;     // RN(1/(range/1000)) when the Markstein division is exact for it, else 0
   // input
   const int64_t* ts;
   const double* val;
@@ -111,6 +115,18 @@ __global__ void __launch_bounds__(256) series_offsets_kernel(const uint32_t* __r
 
 // ---------------------------------------------------------------------------------------------
 // K2 fast path.
+//
+// One warp owns one series at a time.  Per 64-row block: 128-bit coalesced loads (prefetched one
+// block ahead in registers) -> SeriesNormalize (NaN rows dropped by ballot compaction, offset added)
+// -> append to the warp's shared-memory ring (ordinal = index after filtering) -> reset/change bits
+// of the new ordinals by ballot -> every eval step whose window can no longer change is evaluated,
+// one step per lane: window end/start by guess-and-walk on the ring, range function from the ring.
+//
+// TS32: the ring keeps timestamps as uint32 "ms since (start - range)", clamped to [0, span+1].
+// A sample at or before start-range can never be inside a window (windows are (t-range, t] with
+// t >= start) and a sample after `end` can never be either, so clamped samples only ever act as
+// "before everything" / "after everything" sentinels; all in-window arithmetic is exact.  The host
+// selects TS32 when end - start + range < 2^31 ms (24.8 days), else the int64 ring.
 // ---------------------------------------------------------------------------------------------
 struct BlockRegs {  // one lane's share (2 rows) of a 64-row block
   int64_t t0, t1;
@@ -140,15 +156,19 @@ __device__ __forceinline__ BlockRegs load_block(const RangeArgs& a, uint64_t blk
   return b;
 }
 
-template <int FN, int RING>
-struct SeriesState {
-  // warp-uniform
+__device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
+  const int lo = __shfl_sync(0xffffffffu, (int)(v & 0xffffffffll), src);
+  const int hi = __shfl_sync(0xffffffffu, (int)(v >> 32), src);
+  return ((int64_t)hi << 32) | (uint32_t)lo;
+}
+
+struct SeriesState {  // warp-uniform
   uint32_t j_cnt;    // samples inserted so far (ordinal space after NaN filtering)
   uint32_t base_lo;  // lower bound of every future window start
   int32_t base_hi;   // lower bound (index) of every future window end
   int32_t stride_lo, stride_hi;
-  int64_t k_next;    // next global step to evaluate
-  int64_t kf;        // first step the reference evaluates for this series (T = none)
+  int32_t k_next;    // next global step to evaluate
+  int32_t kf;        // first step the reference evaluates for this series (T = none)
   uint32_t vword;    // validity bits of the current aligned 32-step group
   uint32_t lrs;      // calculate_range's last_range_start (for the overshoot check)
   uint32_t max_c0;   // max cursor start (range_start_index + start_delta) feeding a non-empty window
@@ -156,17 +176,42 @@ struct SeriesState {
   bool any_nonempty;
 };
 
+template <bool TS32>
+struct TimeDom;
+template <>
+struct TimeDom<true> {
+  using type = uint32_t;
+  // ms since (start - range), clamped to [0, rel_max]
+  static __device__ __forceinline__ uint32_t conv(int64_t t_abs, const RangeArgs& a) {
+    const int64_t d = t_abs - a.tb;
+    return d <= 0 ? 0u : (d > (int64_t)a.rel_max ? a.rel_max : (uint32_t)d);
+  }
+  static __device__ __forceinline__ uint32_t tlo(const RangeArgs& a, int32_t k) { return (uint32_t)k * (uint32_t)a.interval; }
+  static __device__ __forceinline__ uint32_t range(const RangeArgs& a) { return (uint32_t)a.range; }
+};
+template <>
+struct TimeDom<false> {
+  using type = int64_t;
+  static __device__ __forceinline__ int64_t conv(int64_t t_abs, const RangeArgs&) { return t_abs; }
+  static __device__ __forceinline__ int64_t tlo(const RangeArgs& a, int32_t k) { return a.start + (int64_t)k * a.interval - a.range; }
+  static __device__ __forceinline__ int64_t range(const RangeArgs& a) { return a.range; }
+};
+
 // Evaluate global steps [k_a, k_b) (inside one aligned group of 32); lane = k & 31.
-template <int FN, int RING>
-__device__ __forceinline__ void process_steps(const RangeArgs& a, SeriesState<FN, RING>& st, const RingAcc<RING>& acc,
-                                              double* out_s, uint32_t* vw_s, int64_t k_a, int64_t k_b, int64_t kl,
+template <int FN, int RING, bool TS32>
+__device__ __forceinline__ void process_steps(const RangeArgs& a, SeriesState& st, const RingAcc<RING, TS32>& acc,
+                                              double* out_lane, uint32_t* vw_s, int32_t k_a, int32_t k_b, int32_t kl,
                                               int lane) {
-  const int64_t k = (k_a & ~31ll) + lane;
+  using TD = TimeDom<TS32>;
+  using time_type = typename TD::type;
+  const int32_t kg = k_a & ~31;
+  const int32_t k = kg + lane;
   const bool active = (k >= k_a) && (k < k_b);
-  const int idx = (int)(k - k_a);
-  const int n_act = (int)(k_b - k_a);
-  const int64_t te = a.start + k * a.interval;
-  const int64_t tlo = te - a.range;
+  const int idx = k - k_a;
+  const int n_act = k_b - k_a;
+  const time_type tlo = TD::tlo(a, k);
+  const time_type rng = TD::range(a);
+  const time_type te = tlo + rng;
   int32_t hi = st.base_hi;
   uint32_t lo = st.base_lo;
   if (active && st.j_cnt > 0) {
@@ -189,7 +234,7 @@ __device__ __forceinline__ void process_steps(const RangeArgs& a, SeriesState<FN
   const bool in_grid = active && (k >= st.kf) && (k <= kl);
   double r = 0.0;
   bool ok = false;
-  if (in_grid) ok = eval_window<FN>(acc, lo, l, te, a.range, a.p0, a.p1, r);
+  if (in_grid) ok = eval_window<FN>(acc, lo, l, te, rng, a.p0, a.p1, a.rcp_rs, r);
   if (!ok) r = 0.0;
 
   // --- calculate_range cursor-overshoot watch -----------------------------------
@@ -198,7 +243,8 @@ __device__ __forceinline__ void process_steps(const RangeArgs& a, SeriesState<FN
   // whose following step has a non-empty true window; compared with m at the end of the series.
   const bool nonempty = in_grid && l > 0;
   const uint32_t ne_mask = __ballot_sync(0xffffffffu, nonempty);
-  {
+  const int last = (k_b - 1) & 31;
+  if (ne_mask) {
     const uint32_t before = ne_mask & ((1u << lane) - 1u);
     const int src = before ? (31 - __clz(before)) : 0;
     const uint32_t lo_src = __shfl_sync(0xffffffffu, lo, src);
@@ -206,57 +252,65 @@ __device__ __forceinline__ void process_steps(const RangeArgs& a, SeriesState<FN
     const bool brk = (hi + 1 < (int32_t)st.j_cnt);  // a sample newer than the window end exists
     const uint32_t rsi = (brk && lo > 0) ? lo - 1 : lo;
     const uint32_t c0 = nonempty ? (rsi + (lo - my_lrs)) : 0u;  // empty window => start_delta = 0 < m
-    const int last = (int)((k_b - 1) & 31);
     const bool next_ne = (ne_mask >> ((lane + 1) & 31)) & 1u;
     uint32_t watch = (lane < last && next_ne) ? c0 : 0u;
     if (idx == 0 && nonempty) watch = max(watch, st.carry_c0);  // previous group's last step precedes me
-    st.max_c0 = max(st.max_c0, __reduce_max_sync(0xffffffffu, watch));
+    // only a cursor start at or beyond the samples seen so far can ever reach m (m >= j_cnt)
+    if (__any_sync(0xffffffffu, watch >= st.j_cnt)) st.max_c0 = max(st.max_c0, __reduce_max_sync(0xffffffffu, watch));
     st.carry_c0 = __shfl_sync(0xffffffffu, c0, last);
-    if (ne_mask) {
-      st.lrs = __shfl_sync(0xffffffffu, lo, 31 - __clz(ne_mask));
-      st.any_nonempty = true;
-    }
+    st.lrs = __shfl_sync(0xffffffffu, lo, 31 - __clz(ne_mask));
+    st.any_nonempty = true;
+  } else {
+    st.carry_c0 = 0;
   }
 
   // --- outputs -------------------------------------------------------------------------------------
-  if (active) out_s[k] = r;
+  if (active) out_lane[kg] = r;
   st.vword |= __ballot_sync(0xffffffffu, ok);
-  if (((k_b & 31) == 0 || k_b == a.T)) {
+  if ((k_b & 31) == 0 || k_b == (int32_t)a.T) {
     if (lane == 0) vw_s[(k_b - 1) >> 5] = st.vword;
     st.vword = 0;
   }
 
   // --- advance the warp-uniform search bases ------------------------------------------------------
   if (st.j_cnt > 0) {
-    const int last = (int)((k_b - 1) & 31);
     const int32_t nhi = __shfl_sync(0xffffffffu, hi, last);
     const uint32_t nlo = __shfl_sync(0xffffffffu, lo, last);
-    st.stride_hi = (nhi - st.base_hi + n_act / 2) / n_act;
-    st.stride_lo = (int32_t)(nlo - st.base_lo + (uint32_t)n_act / 2) / n_act;
+    const int32_t dh = nhi - st.base_hi + (n_act >> 1), dl = (int32_t)(nlo - st.base_lo) + (n_act >> 1);
+    st.stride_hi = (n_act == 32) ? (dh >> 5) : dh / n_act;
+    st.stride_lo = (n_act == 32) ? (dl >> 5) : dl / n_act;
     st.base_hi = nhi;
     st.base_lo = nlo;
   }
 }
 
-template <int FN, int RING>
+template <int FN, int RING, bool TS32>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) range_fast_kernel(const RangeArgs a) {
+  using TD = TimeDom<TS32>;
+  using time_type = typename TD::type;
   constexpr int FW = RING / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int64_t* rts = reinterpret_cast<int64_t*>(smem_raw) + warp * RING;
-  double* rval = reinterpret_cast<double*>(smem_raw + (size_t)kWarpsPerCta * RING * 8) + warp * RING;
-  uint32_t* rfl = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kWarpsPerCta * RING * 16) + warp * FW;
-  const RingAcc<RING> acc{rts, rval, rfl};
+  // smem: [warps][RING] val f64 | [warps][RING] ts | [kRcpTable] f64 | [warps][FW] flag words
+  double* rval = reinterpret_cast<double*>(smem_raw) + warp * RING;
+  time_type* rts = reinterpret_cast<time_type*>(smem_raw + (size_t)kWarpsPerCta * RING * 8) + warp * RING;
+  double* rcp_tab = reinterpret_cast<double*>(smem_raw + (size_t)kWarpsPerCta * RING * (8 + sizeof(time_type)));
+  uint32_t* rfl = reinterpret_cast<uint32_t*>(rcp_tab + kRcpTable) + warp * FW;
+  for (int i = threadIdx.x; i < kRcpTable; i += blockDim.x) rcp_tab[i] = (i > 0) ? 1.0 / (double)i : 0.0;
+  __syncthreads();
+  const RingAcc<RING, TS32> acc{rts, rval, rfl, rcp_tab};
   const uint32_t lt = (1u << lane) - 1u;
   const uint32_t total_warps = gridDim.x * kWarpsPerCta;
+  const int32_t T = (int32_t)a.T;
 
   for (uint32_t s = blockIdx.x * kWarpsPerCta + warp; s < a.n_series; s += total_warps) {
     const uint64_t row0 = a.offsets[s], row1 = a.offsets[s + 1];
-    double* out_s = a.out + (size_t)s * (size_t)a.T;
+    double* out_lane = a.out + (size_t)s * (size_t)T + lane;
     uint32_t* vw_s = a.valid + (size_t)s * a.Tw;
-    SeriesState<FN, RING> st;
+    SeriesState st;
     st.j_cnt = 0; st.base_lo = 0; st.base_hi = -1; st.stride_lo = 1; st.stride_hi = 1;
-    st.k_next = 0; st.kf = a.T; st.vword = 0; st.lrs = 0; st.max_c0 = 0; st.carry_c0 = 0; st.any_nonempty = false;
+    st.k_next = 0; st.kf = T; st.vword = 0; st.lrs = 0; st.max_c0 = 0; st.carry_c0 = 0; st.any_nonempty = false;
+    int64_t last_ts = 0;  // exact (absolute, offset applied) timestamp of the newest surviving sample
     bool defer = false;
 
     uint64_t blk = row0 & ~1ull;  // 16-byte aligned pair boundary
@@ -270,14 +324,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) range_fast_kernel(const Ran
       const bool k0 = cur.in0 && !(a.filter_nan && isnan(cur.v0));
       const bool k1 = cur.in1 && !(a.filter_nan && isnan(cur.v1));
       const uint32_t b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
-      const uint32_t j0 = st.j_cnt;
-      const uint32_t pos0 = j0 + __popc(b0 & lt) + __popc(b1 & lt);
-      const uint32_t pos1 = pos0 + (k0 ? 1u : 0u);
-      if (k0) { rts[pos0 & (RING - 1)] = cur.t0 + a.offset; rval[pos0 & (RING - 1)] = cur.v0; }
-      if (k1) { rts[pos1 & (RING - 1)] = cur.t1 + a.offset; rval[pos1 & (RING - 1)] = cur.v1; }
-      st.j_cnt = j0 + __popc(b0) + __popc(b1);
-      __syncwarp();
-      if (st.j_cnt != j0) {
+      const uint32_t any = b0 | b1;
+      if (any) {
+        const int64_t t0 = cur.t0 + a.offset, t1 = cur.t1 + a.offset;
+        const uint32_t j0 = st.j_cnt;
+        const uint32_t pos0 = j0 + __popc(b0 & lt) + __popc(b1 & lt);
+        const uint32_t pos1 = pos0 + (k0 ? 1u : 0u);
+        if (k0) { rts[pos0 & (RING - 1)] = TD::conv(t0, a); rval[pos0 & (RING - 1)] = cur.v0; }
+        if (k1) { rts[pos1 & (RING - 1)] = TD::conv(t1, a); rval[pos1 & (RING - 1)] = cur.v1; }
+        st.j_cnt = j0 + __popc(b0) + __popc(b1);
+        last_ts = shfl_i64(k1 ? t1 : t0, 31 - __clz(any));
+        __syncwarp();
         if constexpr (FnTraits<FN>::kUsesFlags) {
           // reset/change bits of the new ordinals, one aligned 32-bit word per pass
           for (uint32_t wb = j0 & ~31u; wb < st.j_cnt; wb += 32) {
@@ -290,27 +347,35 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) range_fast_kernel(const Ran
           __syncwarp();
         }
         if (j0 == 0) {  // first surviving sample: RangeManipulate start trimming (range_manipulate.rs:714-725)
-          const int64_t first_ts = acc.t(0);
+          const int64_t first_ts = shfl_i64(k0 ? t0 : t1, __ffs(any) - 1);
           const int64_t rem = rem_euclid(first_ts - a.start, a.interval);
           const int64_t first_aligned = rem == 0 ? first_ts : first_ts + (a.interval - rem);
           const int64_t s2 = a.start > first_aligned ? a.start : first_aligned;
           const int64_t kf = (s2 - a.start) / a.interval;
-          st.kf = kf < a.T ? kf : a.T;
+          st.kf = kf < (int64_t)T ? (int32_t)kf : T;
         }
-        // steps whose window can no longer change and that the end-trim cannot remove
-        const int64_t ts_cur = acc.t(st.j_cnt - 1);
-        int64_t k_fin = floor_div(ts_cur - a.start, a.interval);
-        k_fin = k_fin < 0 ? 0 : (k_fin > a.T ? a.T : k_fin);
+        // steps whose window can no longer change and that the end-trim cannot remove:
+        // t_k <= ts_cur - interval  <=>  k < floor((ts_cur - start) / interval)
+        int32_t k_fin;
+        if constexpr (TS32) {
+          const uint32_t rel = TD::conv(last_ts, a);
+          k_fin = rel >= (uint32_t)a.range ? (int32_t)((rel - (uint32_t)a.range) / (uint32_t)a.interval) : 0;
+        } else {
+          const int64_t kk = floor_div(last_ts - a.start, a.interval);
+          k_fin = kk < 0 ? 0 : (kk > (int64_t)T ? T : (int32_t)kk);
+        }
+        k_fin = k_fin > T ? T : k_fin;
         while (st.k_next < k_fin) {
           if (st.j_cnt - st.base_lo > (uint32_t)(RING - 32)) { defer = true; break; }
-          int64_t g_end = (st.k_next | 31ll) + 1; if (g_end > k_fin) g_end = k_fin;
-          process_steps<FN, RING>(a, st, acc, out_s, vw_s, st.k_next, g_end, a.T - 1, lane);
+          int32_t g_end = (st.k_next | 31) + 1;
+          if (g_end > k_fin) g_end = k_fin;
+          process_steps<FN, RING, TS32>(a, st, acc, out_lane, vw_s, st.k_next, g_end, T - 1, lane);
           st.k_next = g_end;
         }
       }
       // ---- ring pressure: drop samples no future window can reach, then make room for 64 more ------
       if (!defer && blk_next < row1 && st.j_cnt + 64u - st.base_lo > (uint32_t)(RING - 32)) {
-        const int64_t tlo_next = a.start + st.k_next * a.interval - a.range;
+        const time_type tlo_next = TD::tlo(a, st.k_next < T ? st.k_next : T - 1);
         while (st.base_lo < st.j_cnt) {
           const uint32_t j = st.base_lo + lane;
           const bool dead = (j < st.j_cnt) && (acc.t(j) <= tlo_next);
@@ -327,18 +392,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) range_fast_kernel(const Ran
 
     if (!defer) {
       // ---- end of stream: RangeManipulate end trimming (range_manipulate.rs:722-728) --------------
-      int64_t kl = -1;
-      if (st.j_cnt > 0) {
-        const int64_t last_ts = acc.t(st.j_cnt - 1);
+      int32_t kl = -1;
+      if (st.j_cnt > 0 && st.kf < T) {
         const int64_t last_aligned = ((last_ts + a.range) / a.interval) * a.interval;
         const int64_t e2 = a.end < last_aligned ? a.end : last_aligned;
-        const int64_t s2 = a.start + st.kf * a.interval;
-        if (st.kf < a.T && e2 >= s2) kl = floor_div(e2 - a.start, a.interval);
+        const int64_t s2 = a.start + (int64_t)st.kf * a.interval;
+        if (e2 >= s2) {
+          const int64_t kk = floor_div(e2 - a.start, a.interval);
+          kl = kk >= (int64_t)T ? T - 1 : (int32_t)kk;
+        }
       }
-      while (st.k_next < a.T) {
+      while (st.k_next < T) {
         if (st.j_cnt - st.base_lo > (uint32_t)(RING - 32)) { defer = true; break; }
-        int64_t g_end = (st.k_next | 31ll) + 1; if (g_end > a.T) g_end = a.T;
-        process_steps<FN, RING>(a, st, acc, out_s, vw_s, st.k_next, g_end, kl, lane);
+        int32_t g_end = (st.k_next | 31) + 1;
+        if (g_end > T) g_end = T;
+        process_steps<FN, RING, TS32>(a, st, acc, out_lane, vw_s, st.k_next, g_end, kl, lane);
         st.k_next = g_end;
       }
       // cursor-overshoot quirk possible -> exact slow path decides
@@ -346,7 +414,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) range_fast_kernel(const Ran
       // "ignore this if all ranges are empty" (range_manipulate.rs:641-643): absent_over_time is the only
       // function that yields Some on an empty window, so it alone needs the series-level veto.
       if (FN == B2P_FN_ABSENT_OVER_TIME && !defer && !st.any_nonempty) {
-        for (int64_t k = lane; k < a.T; k += 32) out_s[k] = 0.0;
+        for (int32_t k = lane; k < T; k += 32) out_lane[k - lane] = 0.0;
         for (uint32_t w = lane; w < a.Tw; w += 32) vw_s[w] = 0u;
       }
     }
@@ -475,7 +543,7 @@ __global__ void __launch_bounds__(128) range_slow_kernel(const RangeArgs a) {
       if (k >= kf && k <= kl) {
         const unsigned long long pk = wins[k];
         ok = eval_window<FN>(acc, (uint32_t)(pk & 0xffffffffull), (uint32_t)(pk >> 32), a.start + k * a.interval,
-                             a.range, a.p0, a.p1, r);
+                             a.range, a.p0, a.p1, 0.0, r);
         if (ok) out_s[k] = r;
       }
       const uint32_t word = __ballot_sync(0xffffffffu, ok);
@@ -500,7 +568,7 @@ __global__ void __launch_bounds__(128) range_udf_kernel(const int64_t* __restric
     const int64_t te = eval_ts ? eval_ts[i] : 0;
     double r = 0.0;
     const bool ok =
-        eval_window<FN>(acc, (uint32_t)(pk & 0xffffffffull), (uint32_t)(pk >> 32), te, range_length, p0, p1, r);
+        eval_window<FN>(acc, (uint32_t)(pk & 0xffffffffull), (uint32_t)(pk >> 32), te, range_length, p0, p1, 0.0, r);
     out[i] = ok ? r : 0.0;
     valid[i] = ok ? 1 : 0;
   }

@@ -97,7 +97,11 @@ class Context:
             raise B2PError(rc, self._L.b2p_last_error().decode())
 
     def set_stream(self, cuda_stream_ptr: Optional[int]):
+        """Enqueue on the given cudaStream_t; 0/None is the legacy default stream."""
         self._check(self._L.b2p_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def use_own_stream(self):
+        self._check(self._L.b2p_use_own_stream(self._h))
 
     def use_torch_stream(self):
         import torch

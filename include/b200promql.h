@@ -124,8 +124,10 @@ B2P_API b2p_ctx* b2p_create(int device);            /* NULL on failure (see b2p_
 B2P_API void b2p_destroy(b2p_ctx* ctx);
 B2P_API const char* b2p_last_error(void);
 B2P_API const char* b2p_version(void);
-/* Use an existing cudaStream_t (e.g. the caller's current stream); NULL restores the context's own. */
+/* Enqueue on an existing cudaStream_t (e.g. the caller's current stream); NULL is the legacy default
+ * stream.  b2p_use_own_stream() goes back to the context's private non-blocking stream. */
 B2P_API int b2p_set_stream(b2p_ctx* ctx, void* cuda_stream);
+B2P_API int b2p_use_own_stream(b2p_ctx* ctx);
 /* Wait for the stream, finish slow-path fix-ups, surface deferred errors (B2P_E_UNSORTED, ...). */
 B2P_API int b2p_sync(b2p_ctx* ctx);
 B2P_API int64_t b2p_num_steps(int64_t start, int64_t end, int64_t interval);

@@ -276,6 +276,52 @@ def test_every_function_matches_oracle_on_irregular_series(ctx, fn):
         assert_close(out, e_out, gv, ev, f"{fn} shape {qi}", bit_exact=fn in BIT_EXACT)
 
 
+def test_int64_ring_path_on_spans_over_24_days(ctx):
+    """end - start + range >= 2^31 ms selects the int64 ring variant of the fused kernel."""
+    from greptimedb_b200 import make_params
+    rng = np.random.default_rng(99)
+    day = 86_400_000
+    ts_l, val_l, offs = [], [], [0]
+    for s in range(40):
+        n = int(rng.integers(0, 300))
+        t = 1_700_000_000_000 + np.sort(rng.integers(0, 40 * day, n)).astype(np.int64)
+        t = np.unique(t)
+        v = np.cumsum(rng.random(t.size) * 5)
+        v[rng.random(t.size) < 0.05] = np.nan
+        ts_l.append(t)
+        val_l.append(v)
+        offs.append(offs[-1] + t.size)
+    ts, val, offsets = np.concatenate(ts_l), np.concatenate(val_l), np.array(offs, np.uint64)
+    for fn in ("rate", "avg_over_time", "resets", "deriv", "irate"):
+        p = make_params(fn, 1_700_000_000_000, 1_700_000_000_000 + 40 * day, 3_600_000, 2 * day)
+        out, valid, ets = ctx.range_eval(p, ts, val, offsets=offsets)
+        op = orc.make_params(fn, 1_700_000_000_000, 1_700_000_000_000 + 40 * day, 3_600_000, 2 * day)
+        e_out, e_valid = orc.range_query(op, ts, val, None, offsets)
+        assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size),
+                     f"ts64 {fn}", bit_exact=fn in BIT_EXACT)
+
+
+def test_rate_is_bit_exact_against_the_rescan_oracle(ctx):
+    """The two-FMA divisions (by window length, by range seconds) must round exactly like IEEE division."""
+    from greptimedb_b200 import make_params
+    S, N, T0 = 256, 1000, 1_700_000_000_000
+    for jitter, resets, rng_ms in ((1000, 1, 300_000), (0, 0, 300_000), (977, 1, 77_777), (1000, 0, 1_000_000)):
+        ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, jitter, resets, 0x5EED)
+        p = make_params("rate", T0, T0 + 999 * 15_000, 15_000, rng_ms)
+        out, valid, ets = ctx.range_eval_n(p, ts, val, sid, None, S)
+        vb = orc.valid_to_bool(valid, ets.size)
+        # oracle, rescan variant, window by window
+        for s in range(0, S, 37):
+            o = s * N
+            off, ln, s2, e2 = orc.calculate_range(ts[o:o + N], T0, T0 + 999 * 15_000, 15_000, rng_ms)
+            ets_s = np.arange(s2, e2 + 1, 15_000)
+            e, ev = orc.range_udf("rate", ts[o:o + N], val[o:o + N], np.stack([off, ln], 1), ets_s, rng_ms, rescan=True)
+            k0 = (s2 - T0) // 15_000
+            got = out[s, k0:k0 + e.size]
+            assert (vb[s, k0:k0 + e.size] == ev).all()
+            assert (got.view(np.uint64)[ev] == e.view(np.uint64)[ev]).all(), (jitter, resets, rng_ms, s)
+
+
 def test_nan_filter_off_passes_nan_through(ctx):
     from greptimedb_b200 import make_params
     ts, val, offsets = make_irregular(77, 24)
