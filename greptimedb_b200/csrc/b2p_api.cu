@@ -410,6 +410,7 @@ int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts,
     memcpy(&bits, &rs, 8);
     const bool all_ones = (bits & 0x000fffffffffffffull) == 0x000fffffffffffffull;
     a.rcp_rs = (p->range > 0 && !all_ones) ? 1.0 / rs : 0.0;
+    a.range_secs = rs;
   }
   a.ts = ts; a.val = val; a.offsets = offsets; a.n_rows = n_rows; a.n_series = n_series;
   a.out = out; a.valid = valid_words;

@@ -20,6 +20,9 @@
 namespace b2p {
 
 constexpr int kWarpsPerCta = 8;
+#ifndef B2P_FAST_MIN_BLOCKS
+#define B2P_FAST_MIN_BLOCKS 3  // resident CTAs per SM the fused kernel is register-budgeted for
+#endif
 
 // Device-side status block, reset before every range/instant call.
 struct Status {
@@ -42,6 +45,7 @@ struct RangeArgs {
   int64_t tb;        // start - range: origin of the uint32 timestamps
   uint32_t rel_max;  // range + (T-1)*interval + 1: clamp for samples after `end`
   double rcp_rs;     // RN(1/(range/1000)) when the Markstein division is exact for it, else 0
+  double range_secs; // (double)range / 1000.0
   // input
   const int64_t* ts;
   const double* val;
@@ -173,6 +177,7 @@ struct SeriesState {  // warp-uniform
   uint32_t lrs;      // calculate_range's last_range_start (for the overshoot check)
   uint32_t max_c0;   // max cursor start (range_start_index + start_delta) feeding a non-empty window
   uint32_t carry_c0; // c0 of the last step of the previous group
+  uint32_t last_flag;  // ordinal of the newest set reset/change bit (0 = none yet)
   bool any_nonempty;
 };
 
@@ -184,7 +189,10 @@ struct TimeDom<true> {
   // ms since (start - range), clamped to [0, rel_max]
   static __device__ __forceinline__ uint32_t conv(int64_t t_abs, const RangeArgs& a) {
     const int64_t d = t_abs - a.tb;
-    return d <= 0 ? 0u : (d > (int64_t)a.rel_max ? a.rel_max : (uint32_t)d);
+    const int32_t dh = (int32_t)(d >> 32);
+    const uint32_t dl = (uint32_t)d;
+    const uint32_t in = dl < a.rel_max ? dl : a.rel_max;  // high word 0: plain 32-bit clamp
+    return dh == 0 ? in : (dh < 0 ? 0u : a.rel_max);
   }
   static __device__ __forceinline__ uint32_t tlo(const RangeArgs& a, int32_t k) { return (uint32_t)k * (uint32_t)a.interval; }
   static __device__ __forceinline__ uint32_t range(const RangeArgs& a) { return (uint32_t)a.range; }
@@ -198,14 +206,14 @@ struct TimeDom<false> {
 };
 
 // Evaluate global steps [k_a, k_b) (inside one aligned group of 32); lane = k & 31.
+// out_grp / vw_grp point at this lane's slot of the group and at the group's validity word.
 template <int FN, int RING, bool TS32>
-__device__ __forceinline__ void process_steps(const RangeArgs& a, SeriesState& st, const RingAcc<RING, TS32>& acc,
-                                              double* out_lane, uint32_t* vw_s, int32_t k_a, int32_t k_b, int32_t kl,
+__device__ __forceinline__ void process_steps(const RangeArgs& a, SeriesState& st, RingAcc<RING, TS32>& acc,
+                                              double* out_grp, uint32_t* vw_grp, int32_t k_a, int32_t k_b, int32_t kl,
                                               int lane) {
   using TD = TimeDom<TS32>;
   using time_type = typename TD::type;
-  const int32_t kg = k_a & ~31;
-  const int32_t k = kg + lane;
+  const int32_t k = (k_a & ~31) + lane;
   const bool active = (k >= k_a) && (k < k_b);
   const int idx = k - k_a;
   const int n_act = k_b - k_a;
@@ -214,24 +222,43 @@ __device__ __forceinline__ void process_steps(const RangeArgs& a, SeriesState& s
   const time_type te = tlo + rng;
   int32_t hi = st.base_hi;
   uint32_t lo = st.base_lo;
-  if (active && st.j_cnt > 0) {
-    // window end: last ordinal with ts <= te.  Guess from the previous group's stride, then walk.
-    int32_t g = st.base_hi + (idx + 1) * st.stride_hi;
+  if (st.j_cnt > 0) {
+    // Window end = last ordinal with ts <= te, window start = first ordinal with ts > te - range.
+    // Guess both from the previous group's stride and verify with four predicated ring reads; only when
+    // some lane's guess is wrong does the whole warp take the (divergence-free to enter) walk.
     const int32_t top = (int32_t)st.j_cnt - 1;
+    int32_t g = st.base_hi + (idx + 1) * st.stride_hi;
     g = g > top ? top : g;
-    while (g < top && acc.t((uint32_t)(g + 1)) <= te) ++g;
-    while (g > st.base_hi && acc.t((uint32_t)g) > te) --g;
-    hi = g;
-    // window start: first ordinal with ts > te - range, in [base_lo, hi+1]
     uint32_t q = st.base_lo + (uint32_t)((idx + 1) * st.stride_lo);
-    const uint32_t qtop = (uint32_t)(hi + 1);
-    q = q > qtop ? qtop : q;
-    while (q > st.base_lo && acc.t(q - 1) > tlo) --q;
-    while (q < qtop && acc.t(q) <= tlo) ++q;
-    lo = q;
+    q = q > (uint32_t)(g + 1) ? (uint32_t)(g + 1) : q;
+    bool good = true;
+    if (active) {
+      const bool has_g = g > st.base_hi, has_g1 = g < top;
+      const bool has_q = (int32_t)q <= g, has_qm = q > st.base_lo;
+      const time_type tg = has_g ? acc.t((uint32_t)g) : (time_type)0;
+      const time_type tg1 = has_g1 ? acc.t((uint32_t)(g + 1)) : (time_type)0;
+      const time_type tq = has_q ? acc.t(q) : (time_type)0;
+      const time_type tqm = has_qm ? acc.t(q - 1) : (time_type)0;
+      good = (!has_g || tg <= te) && (!has_g1 || tg1 > te) && (!has_q || tq > tlo) && (!has_qm || tqm <= tlo);
+    }
+    if (!__all_sync(0xffffffffu, good)) {
+      if (active) {
+        while (g < top && acc.t((uint32_t)(g + 1)) <= te) ++g;
+        while (g > st.base_hi && acc.t((uint32_t)g) > te) --g;
+        const uint32_t qtop = (uint32_t)(g + 1);
+        q = q > qtop ? qtop : q;
+        while (q > st.base_lo && acc.t(q - 1) > tlo) --q;
+        while (q < qtop && acc.t(q) <= tlo) ++q;
+      }
+    }
+    if (active) {
+      hi = g;
+      lo = q;
+    }
   }
   const uint32_t l = (active && (int32_t)lo <= hi) ? (uint32_t)(hi + 1 - (int32_t)lo) : 0u;
   const bool in_grid = active && (k >= st.kf) && (k <= kl);
+  acc.no_flags = st.last_flag <= st.base_lo;  // warp-uniform: no reset/change bit can be inside any window
   double r = 0.0;
   bool ok = false;
   if (in_grid) ok = eval_window<FN>(acc, lo, l, te, rng, a.p0, a.p1, a.rcp_rs, r);
@@ -244,48 +271,174 @@ __device__ __forceinline__ void process_steps(const RangeArgs& a, SeriesState& s
   const bool nonempty = in_grid && l > 0;
   const uint32_t ne_mask = __ballot_sync(0xffffffffu, nonempty);
   const int last = (k_b - 1) & 31;
+  const int32_t nhi = __shfl_sync(0xffffffffu, hi, last);
+  const uint32_t nlo = __shfl_sync(0xffffffffu, lo, last);
   if (ne_mask) {
-    const uint32_t before = ne_mask & ((1u << lane) - 1u);
-    const int src = before ? (31 - __clz(before)) : 0;
-    const uint32_t lo_src = __shfl_sync(0xffffffffu, lo, src);
-    const uint32_t my_lrs = before ? lo_src : st.lrs;
+    const uint32_t act_mask = (n_act == 32) ? 0xffffffffu : (((1u << n_act) - 1u) << (k_a & 31));
     const bool brk = (hi + 1 < (int32_t)st.j_cnt);  // a sample newer than the window end exists
     const uint32_t rsi = (brk && lo > 0) ? lo - 1 : lo;
-    const uint32_t c0 = nonempty ? (rsi + (lo - my_lrs)) : 0u;  // empty window => start_delta = 0 < m
-    const bool next_ne = (ne_mask >> ((lane + 1) & 31)) & 1u;
-    uint32_t watch = (lane < last && next_ne) ? c0 : 0u;
-    if (idx == 0 && nonempty) watch = max(watch, st.carry_c0);  // previous group's last step precedes me
+    uint32_t c0, watch;
+    if (ne_mask == act_mask) {  // common: every step of the group has a non-empty window
+      uint32_t prev_lo = __shfl_up_sync(0xffffffffu, lo, 1);
+      if (idx == 0) prev_lo = st.lrs;
+      c0 = active ? rsi + (lo - prev_lo) : 0u;
+      watch = (lane < last) ? c0 : 0u;           // my successor (lane+1) is non-empty
+      if (idx == 0) watch = max(watch, st.carry_c0);
+      st.lrs = nlo;
+    } else {
+      const uint32_t before = ne_mask & ((1u << lane) - 1u);
+      const int src = before ? (31 - __clz(before)) : 0;
+      const uint32_t lo_src = __shfl_sync(0xffffffffu, lo, src);
+      const uint32_t my_lrs = before ? lo_src : st.lrs;
+      c0 = nonempty ? (rsi + (lo - my_lrs)) : 0u;  // empty window => start_delta = 0 < m
+      const bool next_ne = (ne_mask >> ((lane + 1) & 31)) & 1u;
+      watch = (lane < last && next_ne) ? c0 : 0u;
+      if (idx == 0 && nonempty) watch = max(watch, st.carry_c0);
+      st.lrs = __shfl_sync(0xffffffffu, lo, 31 - __clz(ne_mask));
+    }
     // only a cursor start at or beyond the samples seen so far can ever reach m (m >= j_cnt)
     if (__any_sync(0xffffffffu, watch >= st.j_cnt)) st.max_c0 = max(st.max_c0, __reduce_max_sync(0xffffffffu, watch));
     st.carry_c0 = __shfl_sync(0xffffffffu, c0, last);
-    st.lrs = __shfl_sync(0xffffffffu, lo, 31 - __clz(ne_mask));
     st.any_nonempty = true;
   } else {
     st.carry_c0 = 0;
   }
 
   // --- outputs -------------------------------------------------------------------------------------
-  if (active) out_lane[kg] = r;
+  if (active) *out_grp = r;
   st.vword |= __ballot_sync(0xffffffffu, ok);
   if ((k_b & 31) == 0 || k_b == (int32_t)a.T) {
-    if (lane == 0) vw_s[(k_b - 1) >> 5] = st.vword;
+    if (lane == 0) *vw_grp = st.vword;
     st.vword = 0;
   }
 
   // --- advance the warp-uniform search bases ------------------------------------------------------
   if (st.j_cnt > 0) {
-    const int32_t nhi = __shfl_sync(0xffffffffu, hi, last);
-    const uint32_t nlo = __shfl_sync(0xffffffffu, lo, last);
-    const int32_t dh = nhi - st.base_hi + (n_act >> 1), dl = (int32_t)(nlo - st.base_lo) + (n_act >> 1);
-    st.stride_hi = (n_act == 32) ? (dh >> 5) : dh / n_act;
-    st.stride_lo = (n_act == 32) ? (dl >> 5) : dl / n_act;
+    const int sh = (n_act == 32) ? 5 : (32 - __clz(n_act));  // divide by >= n_act: the stride is only a guess
+    st.stride_hi = (nhi - st.base_hi + (n_act >> 1)) >> sh;
+    st.stride_lo = ((int32_t)(nlo - st.base_lo) + (n_act >> 1)) >> sh;
     st.base_hi = nhi;
     st.base_lo = nlo;
   }
 }
 
+// Steady-state variant of process_steps: a whole aligned group of 32 steps, every step inside the
+// series' evaluated grid [kf, kl], ring non-empty.  No per-lane activity predicates; when consecutive
+// steps advance both window edges by exactly one sample (stride 1: step == scrape interval) each lane
+// reads ONE timestamp per edge and gets its neighbour's through a shuffle.
 template <int FN, int RING, bool TS32>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) range_fast_kernel(const RangeArgs a) {
+__device__ __forceinline__ void process_group_full(const RangeArgs& a, SeriesState& st, RingAcc<RING, TS32>& acc,
+                                                   double* out_grp, uint32_t* vw_grp, int32_t k_a, int lane) {
+  using TD = TimeDom<TS32>;
+  using time_type = typename TD::type;
+  using TR = FnTraits<FN>;
+  const int32_t k = k_a + lane;
+  const time_type tlo = TD::tlo(a, k);
+  const time_type rng = TD::range(a);
+  const time_type te = tlo + rng;
+  const int32_t top = (int32_t)st.j_cnt - 1;
+  int32_t g;
+  uint32_t q;
+  time_type t_hi = 0, t_lo = 0;  // ts[g], ts[q] when the guess verified
+  bool good;
+  if (st.stride_hi == 1 && st.stride_lo == 1 && st.base_hi >= 0 && st.base_hi + 33 <= top &&
+      (int32_t)st.base_lo + 32 <= top) {
+    g = st.base_hi + 1 + lane;
+    q = st.base_lo + 1 + (uint32_t)lane;
+    t_hi = acc.t((uint32_t)g);
+    time_type t_hi_next = __shfl_down_sync(0xffffffffu, t_hi, 1);
+    if (lane == 31) t_hi_next = acc.t((uint32_t)(g + 1));
+    const time_type t_lo_prev = acc.t(q - 1);
+    t_lo = __shfl_down_sync(0xffffffffu, t_lo_prev, 1);
+    if (lane == 31) t_lo = acc.t(q);
+    good = (t_hi <= te) && (t_hi_next > te) && (t_lo_prev <= tlo) && (t_lo > tlo) && ((int32_t)q <= g);
+  } else {
+    g = st.base_hi + (lane + 1) * st.stride_hi;
+    g = g > top ? top : g;
+    q = st.base_lo + (uint32_t)((lane + 1) * st.stride_lo);
+    q = q > (uint32_t)(g + 1) ? (uint32_t)(g + 1) : q;
+    const bool has_g = g > st.base_hi, has_g1 = g < top;
+    const bool has_q = (int32_t)q <= g, has_qm = q > st.base_lo;
+    const time_type tg = has_g ? acc.t((uint32_t)g) : (time_type)0;
+    const time_type tg1 = has_g1 ? acc.t((uint32_t)(g + 1)) : (time_type)0;
+    const time_type tq = has_q ? acc.t(q) : (time_type)0;
+    const time_type tqm = has_qm ? acc.t(q - 1) : (time_type)0;
+    good = has_g && has_q && (tg <= te) && (!has_g1 || tg1 > te) && (tq > tlo) && (!has_qm || tqm <= tlo);
+    t_hi = tg;
+    t_lo = tq;
+  }
+  if (!__all_sync(0xffffffffu, good)) {  // some guess missed: every lane walks (zero steps where it was right)
+    while (g < top && acc.t((uint32_t)(g + 1)) <= te) ++g;
+    while (g > st.base_hi && acc.t((uint32_t)g) > te) --g;
+    const uint32_t qtop = (uint32_t)(g + 1);
+    q = q > qtop ? qtop : q;
+    while (q > st.base_lo && acc.t(q - 1) > tlo) --q;
+    while (q < qtop && acc.t(q) <= tlo) ++q;
+    if (g >= 0) t_hi = acc.t((uint32_t)g);
+    t_lo = acc.t(q);
+  }
+  const int32_t hi = g;
+  const uint32_t lo = q;
+  const uint32_t l = ((int32_t)lo <= hi) ? (uint32_t)(hi + 1 - (int32_t)lo) : 0u;
+  acc.no_flags = st.last_flag <= st.base_lo;
+  double r = 0.0;
+  bool ok;
+  if constexpr (TR::kExtrapolated) {
+    ok = l >= 2;
+    if (ok) r = extrapolated_value<FN>(acc, lo, l, t_lo, t_hi, te, rng, a.range_secs, a.rcp_rs);
+  } else {
+    ok = eval_window<FN>(acc, lo, l, te, rng, a.p0, a.p1, a.rcp_rs, r);
+    if (!ok) r = 0.0;
+  }
+
+  // cursor-overshoot watch (see process_steps)
+  const bool nonempty = l > 0;
+  const uint32_t ne_mask = __ballot_sync(0xffffffffu, nonempty);
+  const int32_t nhi = __shfl_sync(0xffffffffu, hi, 31);
+  const uint32_t nlo = __shfl_sync(0xffffffffu, lo, 31);
+  if (ne_mask == 0xffffffffu) {
+    const bool brk = (hi + 1 < (int32_t)st.j_cnt);
+    const uint32_t rsi = (brk && lo > 0) ? lo - 1 : lo;
+    uint32_t prev_lo = __shfl_up_sync(0xffffffffu, lo, 1);
+    if (lane == 0) prev_lo = st.lrs;
+    const uint32_t c0 = rsi + (lo - prev_lo);
+    uint32_t watch = (lane < 31) ? c0 : 0u;
+    if (lane == 0) watch = max(watch, st.carry_c0);
+    if (__any_sync(0xffffffffu, watch >= st.j_cnt)) st.max_c0 = max(st.max_c0, __reduce_max_sync(0xffffffffu, watch));
+    st.carry_c0 = __shfl_sync(0xffffffffu, c0, 31);
+    st.lrs = nlo;
+    st.any_nonempty = true;
+  } else if (ne_mask) {
+    const bool brk = (hi + 1 < (int32_t)st.j_cnt);
+    const uint32_t rsi = (brk && lo > 0) ? lo - 1 : lo;
+    const uint32_t before = ne_mask & ((1u << lane) - 1u);
+    const int src = before ? (31 - __clz(before)) : 0;
+    const uint32_t lo_src = __shfl_sync(0xffffffffu, lo, src);
+    const uint32_t my_lrs = before ? lo_src : st.lrs;
+    const uint32_t c0 = nonempty ? (rsi + (lo - my_lrs)) : 0u;
+    const bool next_ne = (ne_mask >> ((lane + 1) & 31)) & 1u;
+    uint32_t watch = (lane < 31 && next_ne) ? c0 : 0u;
+    if (lane == 0 && nonempty) watch = max(watch, st.carry_c0);
+    if (__any_sync(0xffffffffu, watch >= st.j_cnt)) st.max_c0 = max(st.max_c0, __reduce_max_sync(0xffffffffu, watch));
+    st.carry_c0 = __shfl_sync(0xffffffffu, c0, 31);
+    st.lrs = __shfl_sync(0xffffffffu, lo, 31 - __clz(ne_mask));
+    st.any_nonempty = true;
+  } else {
+    st.carry_c0 = 0;
+  }
+
+  *out_grp = r;
+  const uint32_t vw = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) *vw_grp = vw;
+
+  st.stride_hi = (nhi - st.base_hi + 16) >> 5;
+  st.stride_lo = ((int32_t)(nlo - st.base_lo) + 16) >> 5;
+  st.base_hi = nhi;
+  st.base_lo = nlo;
+}
+
+template <int FN, int RING, bool TS32>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_fast_kernel(const RangeArgs a) {
   using TD = TimeDom<TS32>;
   using time_type = typename TD::type;
   constexpr int FW = RING / 32;
@@ -298,20 +451,44 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) range_fast_kernel(const Ran
   uint32_t* rfl = reinterpret_cast<uint32_t*>(rcp_tab + kRcpTable) + warp * FW;
   for (int i = threadIdx.x; i < kRcpTable; i += blockDim.x) rcp_tab[i] = (i > 0) ? 1.0 / (double)i : 0.0;
   __syncthreads();
-  const RingAcc<RING, TS32> acc{rts, rval, rfl, rcp_tab};
+  RingAcc<RING, TS32> acc{rts, rval, rfl, rcp_tab, false};
   const uint32_t lt = (1u << lane) - 1u;
   const uint32_t total_warps = gridDim.x * kWarpsPerCta;
   const int32_t T = (int32_t)a.T;
 
   for (uint32_t s = blockIdx.x * kWarpsPerCta + warp; s < a.n_series; s += total_warps) {
     const uint64_t row0 = a.offsets[s], row1 = a.offsets[s + 1];
-    double* out_lane = a.out + (size_t)s * (size_t)T + lane;
-    uint32_t* vw_s = a.valid + (size_t)s * a.Tw;
+    double* const out_s = a.out + (size_t)s * (size_t)T;
+    uint32_t* const vw_s = a.valid + (size_t)s * a.Tw;
+    double* out_grp = out_s + lane;  // this lane's slot in the current aligned 32-step group
+    uint32_t* vw_grp = vw_s;         // validity word of the current group
     SeriesState st;
     st.j_cnt = 0; st.base_lo = 0; st.base_hi = -1; st.stride_lo = 1; st.stride_hi = 1;
-    st.k_next = 0; st.kf = T; st.vword = 0; st.lrs = 0; st.max_c0 = 0; st.carry_c0 = 0; st.any_nonempty = false;
+    st.k_next = 0; st.kf = T; st.vword = 0; st.lrs = 0; st.max_c0 = 0; st.carry_c0 = 0; st.last_flag = 0;
+    st.any_nonempty = false;
     int64_t last_ts = 0;  // exact (absolute, offset applied) timestamp of the newest surviving sample
+    int32_t k_fin = 0;    // steps [0, k_fin) can be evaluated with what is in the ring
     bool defer = false;
+
+    // evaluate [k_next, upto) in aligned groups of 32; advances the output cursors
+#define B2P_RUN_STEPS(UPTO, KL)                                                                      \
+    do {                                                                                              \
+      const int32_t upto__ = (UPTO);                                                                  \
+      while (st.k_next < upto__) {                                                                    \
+        if (st.j_cnt - st.base_lo > (uint32_t)(RING - 32)) { defer = true; break; }                   \
+        int32_t g_end = (st.k_next | 31) + 1;                                                         \
+        if (g_end > upto__) g_end = upto__;                                                           \
+        if (g_end - st.k_next == 32 && st.k_next >= st.kf && g_end - 1 <= (KL) && st.j_cnt > 0)       \
+          process_group_full<FN, RING, TS32>(a, st, acc, out_grp, vw_grp, st.k_next, lane);           \
+        else                                                                                          \
+          process_steps<FN, RING, TS32>(a, st, acc, out_grp, vw_grp, st.k_next, g_end, (KL), lane);   \
+        st.k_next = g_end;                                                                            \
+        if ((g_end & 31) == 0) {                                                                      \
+          out_grp += 32;                                                                              \
+          vw_grp += 1;                                                                                \
+        }                                                                                             \
+      }                                                                                               \
+    } while (0)
 
     uint64_t blk = row0 & ~1ull;  // 16-byte aligned pair boundary
     BlockRegs nxt = load_block(a, blk, row0, row1, lane);
@@ -336,13 +513,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) range_fast_kernel(const Ran
         last_ts = shfl_i64(k1 ? t1 : t0, 31 - __clz(any));
         __syncwarp();
         if constexpr (FnTraits<FN>::kUsesFlags) {
-          // reset/change bits of the new ordinals, one aligned 32-bit word per pass
-          for (uint32_t wb = j0 & ~31u; wb < st.j_cnt; wb += 32) {
-            const uint32_t j = wb + lane;
-            bool f = false;
-            if (j >= 1 && j < st.j_cnt) f = flag_pred<FN>(acc.v(j), acc.v(j - 1));
-            const uint32_t word = __ballot_sync(0xffffffffu, f);
-            if (lane == 0) rfl[(wb >> 5) & (FW - 1)] = word;
+          // Does any new sample reset/change against its predecessor?  Each lane tests its own one or two
+          // survivors (predecessor = ring[pos0-1], or its own first sample): one LDS, one ballot.
+          const double prev0 = (pos0 > 0) ? rval[(pos0 - 1) & (RING - 1)] : cur.v0;
+          const bool f0 = k0 && pos0 > 0 && flag_pred<FN>(cur.v0, prev0);
+          const bool f1 = k1 && pos1 > 0 && flag_pred<FN>(cur.v1, k0 ? cur.v0 : prev0);
+          if (__any_sync(0xffffffffu, f0 || f1)) {
+            // rebuild the bit words of the new ordinals, one aligned 32-bit word per ballot
+            for (uint32_t wb = j0 & ~31u; wb < st.j_cnt; wb += 32) {
+              const uint32_t j = wb + lane;
+              bool f = false;
+              if (j >= 1 && j < st.j_cnt) f = flag_pred<FN>(acc.v(j), acc.v(j - 1));
+              const uint32_t word = __ballot_sync(0xffffffffu, f);
+              if (lane == 0) rfl[(wb >> 5) & (FW - 1)] = word;
+              if (word) st.last_flag = wb + 31 - __clz(word);
+            }
+          } else {
+            // no set bit among the new ordinals: clear the words they start (a partially filled word
+            // already holds zeros above the previous j_cnt)
+            const uint32_t w_first = (j0 + 31) >> 5, w_last = (st.j_cnt - 1) >> 5;
+            if (w_first + (uint32_t)lane <= w_last) rfl[(w_first + lane) & (FW - 1)] = 0u;
           }
           __syncwarp();
         }
@@ -356,7 +546,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) range_fast_kernel(const Ran
         }
         // steps whose window can no longer change and that the end-trim cannot remove:
         // t_k <= ts_cur - interval  <=>  k < floor((ts_cur - start) / interval)
-        int32_t k_fin;
         if constexpr (TS32) {
           const uint32_t rel = TD::conv(last_ts, a);
           k_fin = rel >= (uint32_t)a.range ? (int32_t)((rel - (uint32_t)a.range) / (uint32_t)a.interval) : 0;
@@ -365,27 +554,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) range_fast_kernel(const Ran
           k_fin = kk < 0 ? 0 : (kk > (int64_t)T ? T : (int32_t)kk);
         }
         k_fin = k_fin > T ? T : k_fin;
-        while (st.k_next < k_fin) {
-          if (st.j_cnt - st.base_lo > (uint32_t)(RING - 32)) { defer = true; break; }
-          int32_t g_end = (st.k_next | 31) + 1;
-          if (g_end > k_fin) g_end = k_fin;
-          process_steps<FN, RING, TS32>(a, st, acc, out_lane, vw_s, st.k_next, g_end, T - 1, lane);
-          st.k_next = g_end;
-        }
+        // steady state: whole aligned groups only (a partial group waits for the next block)
+        B2P_RUN_STEPS(k_fin & ~31, T - 1);
       }
-      // ---- ring pressure: drop samples no future window can reach, then make room for 64 more ------
+      // ---- ring pressure: evaluate what is final, drop samples no future window can reach -----------
       if (!defer && blk_next < row1 && st.j_cnt + 64u - st.base_lo > (uint32_t)(RING - 32)) {
-        const time_type tlo_next = TD::tlo(a, st.k_next < T ? st.k_next : T - 1);
-        while (st.base_lo < st.j_cnt) {
-          const uint32_t j = st.base_lo + lane;
-          const bool dead = (j < st.j_cnt) && (acc.t(j) <= tlo_next);
-          const uint32_t m = __ballot_sync(0xffffffffu, dead);
-          const uint32_t adv = (m == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~m) - 1);
-          st.base_lo += adv;
-          if (adv < 32u) break;
+        B2P_RUN_STEPS(k_fin, T - 1);  // partial group: frees the ring up to its last window start
+        if (!defer) {
+          const time_type tlo_next = TD::tlo(a, st.k_next < T ? st.k_next : T - 1);
+          while (st.base_lo < st.j_cnt) {
+            const uint32_t j = st.base_lo + lane;
+            const bool dead = (j < st.j_cnt) && (acc.t(j) <= tlo_next);
+            const uint32_t m = __ballot_sync(0xffffffffu, dead);
+            const uint32_t adv = (m == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~m) - 1);
+            st.base_lo += adv;
+            if (adv < 32u) break;
+          }
+          if ((int32_t)st.base_lo - 1 > st.base_hi) st.base_hi = (int32_t)st.base_lo - 1;
+          if (st.j_cnt + 64u - st.base_lo > (uint32_t)(RING - 32)) defer = true;
         }
-        if ((int32_t)st.base_lo - 1 > st.base_hi) st.base_hi = (int32_t)st.base_lo - 1;
-        if (st.j_cnt + 64u - st.base_lo > (uint32_t)(RING - 32)) defer = true;
       }
       blk = blk_next;
     }
@@ -402,19 +589,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) range_fast_kernel(const Ran
           kl = kk >= (int64_t)T ? T - 1 : (int32_t)kk;
         }
       }
-      while (st.k_next < T) {
-        if (st.j_cnt - st.base_lo > (uint32_t)(RING - 32)) { defer = true; break; }
-        int32_t g_end = (st.k_next | 31) + 1;
-        if (g_end > T) g_end = T;
-        process_steps<FN, RING, TS32>(a, st, acc, out_lane, vw_s, st.k_next, g_end, kl, lane);
-        st.k_next = g_end;
-      }
+      B2P_RUN_STEPS(T, kl);
       // cursor-overshoot quirk possible -> exact slow path decides
       if (!defer && st.j_cnt > 0 && st.max_c0 >= st.j_cnt) defer = true;
       // "ignore this if all ranges are empty" (range_manipulate.rs:641-643): absent_over_time is the only
       // function that yields Some on an empty window, so it alone needs the series-level veto.
       if (FN == B2P_FN_ABSENT_OVER_TIME && !defer && !st.any_nonempty) {
-        for (int32_t k = lane; k < T; k += 32) out_lane[k - lane] = 0.0;
+        for (int32_t k = lane; k < T; k += 32) out_s[k] = 0.0;
         for (uint32_t w = lane; w < a.Tw; w += 32) vw_s[w] = 0u;
       }
     }
@@ -424,6 +605,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) range_fast_kernel(const Ran
     }
     __syncwarp();
   }
+#undef B2P_RUN_STEPS
 }
 
 // ---------------------------------------------------------------------------------------------
