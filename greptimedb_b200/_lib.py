@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200promql.so")
+LIB_PATH = os.environ.get("B2P_LIB_PATH") or os.path.join(_HERE, "libb200promql.so")  # override: tuning experiments only
 
 # every symbol include/b200promql.h declares (tests/test_abi.py checks the .so exports them all)
 EXPORTED_SYMBOLS = [

@@ -93,6 +93,11 @@ struct b2p_ctx {
   long long last_slow = 0;
   // host-API staging
   DevBuf h_ts, h_val, h_sid, h_off, h_out, h_valid, h_aux0, h_aux1, h_aux2, h_aux3;
+  // host-API pipeline (double-buffered staging, separate copy streams)
+  bool pipe_ready = false;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
+  DevBuf p_ts[2], p_val[2], p_sid[2], p_off[2], p_out[2], p_valid[2], p_status;
   // group aggregate scratch
   DevBuf g_keys_in, g_keys_out, g_vals_in, g_vals_out, g_goff, g_tmp;
   // column reduce scratch
@@ -297,6 +302,15 @@ void b2p_destroy(b2p_ctx* c) {
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 2; ++j)
       if (c->ev[i][j]) cudaEventDestroy(c->ev[i][j]);
+  for (int i = 0; i < 2; ++i) {
+    for (DevBuf* b : {&c->p_ts[i], &c->p_val[i], &c->p_sid[i], &c->p_off[i], &c->p_out[i], &c->p_valid[i]}) b->release();
+    if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+    if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
+    if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
+  }
+  c->p_status.release();
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   if (c->d_status) cudaFree(c->d_status);
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -367,7 +381,15 @@ int b2p_sync(b2p_ctx* c) {
 
 /* ---- device-pointer API ---------------------------------------------------------------------- */
 
+static int series_offsets_impl(b2p_ctx* c, const uint32_t* sid, uint64_t n_rows, uint32_t n_series, uint32_t sid_base,
+                               uint64_t* offsets);
+
 int b2p_series_offsets_dev(b2p_ctx* c, const uint32_t* sid, uint64_t n_rows, uint32_t n_series, uint64_t* offsets) {
+  return series_offsets_impl(c, sid, n_rows, n_series, 0u, offsets);
+}
+
+static int series_offsets_impl(b2p_ctx* c, const uint32_t* sid, uint64_t n_rows, uint32_t n_series, uint32_t sid_base,
+                               uint64_t* offsets) {
   if (!c || !offsets || (!sid && n_rows)) return fail(B2P_E_INVALID, "NULL argument");
   if (!aligned16(sid)) return fail(B2P_E_INVALID, "sid must be 16-byte aligned");
   DeviceGuard g(c->device);
@@ -377,7 +399,7 @@ int b2p_series_offsets_dev(b2p_ctx* c, const uint32_t* sid, uint64_t n_rows, uin
   if (blocks == 0) blocks = 1;
   CU(cudaMemsetAsync(&c->d_status->k0_errors, 0, sizeof(uint32_t), c->stream));
   stage_begin(c, 0);
-  series_offsets_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(sid, n_rows, n_series, offsets, c->d_status);
+  series_offsets_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(sid, n_rows, n_series, sid_base, offsets, c->d_status);
   c->launches++;
   stage_end(c, 0);
   CU(cudaGetLastError());
@@ -629,19 +651,12 @@ int b2p_synth_fill_dev(b2p_ctx* c, uint64_t series_begin, uint64_t n_series, uin
 
 /* ---- host-pointer API ------------------------------------------------------------------------ */
 
-int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val, const uint32_t* sid,
-                   const uint64_t* offsets_host, uint64_t n_rows, uint32_t n_series, double* out,
-                   uint32_t* valid_words, int64_t* out_ts) {
-  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
-  int64_t T = 0;
-  int rc = check_grid(p, n_series, &T);
-  if (rc) return rc;
-  if (out_ts)
-    for (int64_t k = 0; k < T; ++k) out_ts[k] = p->start + k * p->interval;
-  if (n_series == 0 || T == 0) return B2P_OK;
-  if (!sid && !offsets_host) return fail(B2P_E_INVALID, "need sid or offsets_host");
-  if (!out || !valid_words || ((!ts || !val) && n_rows)) return fail(B2P_E_INVALID, "NULL argument");
-  DeviceGuard g(c->device);
+// One chunk, no overlap: H2D -> K0/K2 -> D2H on the context stream.  sid values are global ids
+// (sid_base is subtracted on the device); offsets_host, when given, is already rebased to the chunk.
+static int range_eval_host_simple(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val,
+                                  const uint32_t* sid, uint32_t sid_base, const uint64_t* offsets_host, uint64_t n_rows,
+                                  uint32_t n_series, int64_t T, double* out, uint32_t* valid_words) {
+  int rc;
   const uint32_t Tw = (uint32_t)((T + 31) / 32);
   const size_t rows = n_rows ? n_rows : 1;
   if ((rc = c->h_ts.ensure(rows * 8 + 16))) return rc;
@@ -657,7 +672,8 @@ int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, con
   } else {
     if ((rc = c->h_sid.ensure(rows * 4 + 16))) return rc;
     CU(cudaMemcpyAsync(c->h_sid.p, sid, n_rows * 4, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = b2p_series_offsets_dev(c, c->h_sid.as<uint32_t>(), n_rows, n_series, c->h_off.as<uint64_t>()))) return rc;
+    if ((rc = series_offsets_impl(c, c->h_sid.as<uint32_t>(), n_rows, n_series, sid_base, c->h_off.as<uint64_t>())))
+      return rc;
   }
   if ((rc = b2p_range_eval_dev(c, p, c->h_ts.as<int64_t>(), c->h_val.as<double>(), c->h_off.as<uint64_t>(), n_rows,
                                n_series, c->h_out.as<double>(), c->h_valid.as<uint32_t>())))
@@ -666,6 +682,162 @@ int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, con
   CU(cudaMemcpyAsync(out, c->h_out.p, (size_t)n_series * (size_t)T * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(valid_words, c->h_valid.p, (size_t)n_series * Tw * 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return B2P_OK;
+}
+
+// first row whose id is >= key in a non-decreasing id column
+static uint64_t lower_bound_sid(const uint32_t* sid, uint64_t n, uint64_t key) {
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if ((uint64_t)sid[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val, const uint32_t* sid,
+                   const uint64_t* offsets_host, uint64_t n_rows, uint32_t n_series, double* out,
+                   uint32_t* valid_words, int64_t* out_ts) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  int64_t T = 0;
+  int rc = check_grid(p, n_series, &T);
+  if (rc) return rc;
+  if (out_ts)
+    for (int64_t k = 0; k < T; ++k) out_ts[k] = p->start + k * p->interval;
+  if (n_series == 0 || T == 0) return B2P_OK;
+  if (!sid && !offsets_host) return fail(B2P_E_INVALID, "need sid or offsets_host");
+  if (!out || !valid_words || ((!ts || !val) && n_rows)) return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  const uint32_t Tw = (uint32_t)((T + 31) / 32);
+
+  // ---- small inputs: one shot -------------------------------------------------------------------
+  constexpr uint64_t kChunkRows = 4u << 20;  // ~84 MB of H2D per chunk
+  if (n_rows <= kChunkRows + kChunkRows / 2 || n_series < 64)
+    return range_eval_host_simple(c, p, ts, val, sid, 0u, offsets_host, n_rows, n_series, T, out, valid_words);
+
+  // ---- large inputs: series chunks, double-buffered; H2D(i+1) | K0+K2(i) | D2H(i-1) overlap -----------
+  const uint64_t avg_rows = n_rows / n_series + 1;
+  uint32_t C = (uint32_t)(kChunkRows / avg_rows);
+  if (C < 64) C = 64;
+  const uint32_t n_chunks = (n_series + C - 1) / C;
+  if (!c->pipe_ready) {
+    bool ok = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 2; ++i) {
+      ok = ok && cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) return fail(B2P_E_CUDA, "pipeline stream/event creation failed");
+    c->pipe_ready = true;
+  }
+  if ((rc = c->p_status.ensure((size_t)n_chunks * sizeof(Status)))) return rc;  // device copies of each chunk's status
+  Status* h_stat = nullptr;
+  CU(cudaMallocHost(&h_stat, (size_t)n_chunks * sizeof(Status)));
+  uint64_t* h_offs[2] = {nullptr, nullptr};
+  if (offsets_host) {
+    for (int i = 0; i < 2; ++i) CU(cudaMallocHost(&h_offs[i], ((size_t)C + 1) * 8));
+  }
+  struct Cleanup {
+    Status* s; uint64_t* o0; uint64_t* o1;
+    ~Cleanup() { if (s) cudaFreeHost(s); if (o0) cudaFreeHost(o0); if (o1) cudaFreeHost(o1); }
+  } cleanup{h_stat, h_offs[0], h_offs[1]};
+
+  // worst-case chunk row count (chunks are whole series)
+  uint64_t max_rows = 0;
+  {
+    uint64_t prev = 0;
+    for (uint32_t i = 0; i < n_chunks; ++i) {
+      const uint64_t s1 = (uint64_t)(i + 1) * C < n_series ? (uint64_t)(i + 1) * C : n_series;
+      const uint64_t r1 = offsets_host ? offsets_host[s1] : lower_bound_sid(sid, n_rows, s1);
+      if (r1 < prev) return fail(B2P_E_UNSORTED, "series-id column is not non-decreasing");
+      if (r1 - prev > max_rows) max_rows = r1 - prev;
+      prev = r1;
+    }
+    if (!offsets_host && prev != n_rows) return fail(B2P_E_UNSORTED, "series id >= n_series");
+  }
+  for (int i = 0; i < 2; ++i) {
+    if ((rc = c->p_ts[i].ensure(max_rows * 8 + 16))) return rc;
+    if ((rc = c->p_val[i].ensure(max_rows * 8 + 16))) return rc;
+    if (!offsets_host && (rc = c->p_sid[i].ensure(max_rows * 4 + 16))) return rc;
+    if ((rc = c->p_off[i].ensure(((size_t)C + 1) * 8))) return rc;
+    if ((rc = c->p_out[i].ensure((size_t)C * (size_t)T * 8))) return rc;
+    if ((rc = c->p_valid[i].ensure((size_t)C * Tw * 4))) return rc;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  uint64_t row_lo = 0;
+  for (uint32_t i = 0; i < n_chunks; ++i) {
+    const int b = (int)(i & 1);
+    const uint32_t s0 = i * C;
+    const uint32_t s1 = (uint64_t)s0 + C < n_series ? s0 + C : n_series;
+    const uint32_t ns = s1 - s0;
+    const uint64_t row_hi = offsets_host ? offsets_host[s1] : lower_bound_sid(sid, n_rows, s1);
+    const uint64_t nr = row_hi - row_lo;
+    // H2D of chunk i may start once chunk i-2's kernels no longer read this buffer pair
+    if (i >= 2) CU(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[b], 0));
+    CU(cudaMemcpyAsync(c->p_ts[b].p, ts + row_lo, nr * 8, cudaMemcpyHostToDevice, c->s_h2d));
+    CU(cudaMemcpyAsync(c->p_val[b].p, val + row_lo, nr * 8, cudaMemcpyHostToDevice, c->s_h2d));
+    if (offsets_host) {
+      if (i >= 2) CU(cudaEventSynchronize(c->ev_h2d[b]));  // the pinned rebase buffer is free again
+      for (uint32_t q = 0; q <= ns; ++q) h_offs[b][q] = offsets_host[s0 + q] - row_lo;
+      CU(cudaMemcpyAsync(c->p_off[b].p, h_offs[b], ((size_t)ns + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
+    } else {
+      CU(cudaMemcpyAsync(c->p_sid[b].p, sid + row_lo, nr * 4, cudaMemcpyHostToDevice, c->s_h2d));
+    }
+    CU(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
+    // compute: after its inputs landed and after chunk i-2's results left the output buffers
+    CU(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
+    if (i >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_d2h[b], 0));
+    if ((rc = reset_status(c))) return rc;
+    if (!offsets_host &&
+        (rc = series_offsets_impl(c, c->p_sid[b].as<uint32_t>(), nr, ns, s0, c->p_off[b].as<uint64_t>())))
+      return rc;
+    if ((rc = b2p_range_eval_dev(c, p, c->p_ts[b].as<int64_t>(), c->p_val[b].as<double>(), c->p_off[b].as<uint64_t>(),
+                                 nr, ns, c->p_out[b].as<double>(), c->p_valid[b].as<uint32_t>())))
+      return rc;
+    CU(cudaMemcpyAsync(c->p_status.as<Status>() + i, c->d_status, sizeof(Status), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaEventRecord(c->ev_comp[b], c->stream));
+    // D2H
+    CU(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[b], 0));
+    CU(cudaMemcpyAsync(out + (size_t)s0 * (size_t)T, c->p_out[b].p, (size_t)ns * (size_t)T * 8, cudaMemcpyDeviceToHost,
+                       c->s_d2h));
+    CU(cudaMemcpyAsync(valid_words + (size_t)s0 * Tw, c->p_valid[b].p, (size_t)ns * Tw * 4, cudaMemcpyDeviceToHost,
+                       c->s_d2h));
+    CU(cudaEventRecord(c->ev_d2h[b], c->s_d2h));
+    row_lo = row_hi;
+  }
+  CU(cudaMemcpyAsync(h_stat, c->p_status.p, (size_t)n_chunks * sizeof(Status), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->s_d2h));
+  c->pending_range = false;
+  // per-chunk verdicts; a chunk whose slow path ran out of arena is redone alone (b2p_sync grows the arena)
+  long long slow_total = 0;
+  row_lo = 0;
+  for (uint32_t i = 0; i < n_chunks; ++i) {
+    const uint32_t s0 = i * C;
+    const uint32_t s1 = (uint64_t)s0 + C < n_series ? s0 + C : n_series;
+    const uint64_t row_hi = offsets_host ? offsets_host[s1] : lower_bound_sid(sid, n_rows, s1);
+    const Status st = h_stat[i];
+    slow_total += st.slow_count;
+    if (st.k0_errors & 1u) return fail(B2P_E_UNSORTED, "series-id column is not non-decreasing");
+    if (st.k0_errors & 2u) return fail(B2P_E_UNSORTED, "series id >= n_series");
+    if (st.arena_overflow) {
+      std::string tmp_offs;
+      const uint64_t* offs_chunk = nullptr;
+      if (offsets_host) {
+        tmp_offs.resize(((size_t)(s1 - s0) + 1) * 8);
+        uint64_t* o = reinterpret_cast<uint64_t*>(&tmp_offs[0]);
+        for (uint32_t q = 0; q <= s1 - s0; ++q) o[q] = offsets_host[s0 + q] - row_lo;
+        offs_chunk = o;
+      }
+      if ((rc = range_eval_host_simple(c, p, ts + row_lo, val + row_lo, sid ? sid + row_lo : nullptr, s0, offs_chunk,
+                                       row_hi - row_lo, s1 - s0, T, out + (size_t)s0 * (size_t)T,
+                                       valid_words + (size_t)s0 * Tw)))
+        return rc;
+    }
+    row_lo = row_hi;
+  }
+  c->last_slow = slow_total;
   return B2P_OK;
 }
 

@@ -79,8 +79,8 @@ __device__ __forceinline__ int64_t rem_euclid(int64_t a, int64_t b) {
 // non-decreasing (the reference requires the same ordering, series_divide.rs:410-440).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) series_offsets_kernel(const uint32_t* __restrict__ sid, uint64_t n_rows,
-                                                             uint32_t n_series, uint64_t* __restrict__ offsets,
-                                                             Status* status) {
+                                                             uint32_t n_series, uint32_t sid_base,
+                                                             uint64_t* __restrict__ offsets, Status* status) {
   const uint64_t n4 = (n_rows + 3) / 4;
   for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t r0 = q * 4;
@@ -92,12 +92,12 @@ __global__ void __launch_bounds__(256) series_offsets_kernel(const uint32_t* __r
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = (r0 + i < n_rows) ? sid[r0 + i] : 0u;
     }
-    uint32_t prev = (r0 == 0) ? 0u : sid[r0 - 1];
+    uint32_t prev = (r0 == 0) ? 0u : sid[r0 - 1] - sid_base;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint64_t r = r0 + i;
       if (r >= n_rows) break;
-      const uint32_t cur = v[i];
+      const uint32_t cur = v[i] - sid_base;  // ids below sid_base wrap to >= n_series and are flagged
       if (cur >= n_series) {
         atomicOr(&status->k0_errors, 2u);
       } else if (r == 0) {

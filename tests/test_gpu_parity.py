@@ -400,6 +400,29 @@ def test_bench_shape_matches_oracle_both_variants(ctx):
         assert gv.sum() > 0.97 * S * 1000
 
 
+def test_pipelined_host_path_matches_oracle(ctx):
+    """> 6 M rows makes b2p_range_eval split the series into double-buffered chunks (H2D | kernels | D2H overlap)."""
+    from greptimedb_b200 import make_params
+    S, N, T0 = 9000, 1000, 1_700_000_000_000
+    ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, 1000, 1, 0x5EED)
+    val[::1013] = np.nan
+    offsets = np.arange(S + 1, dtype=np.uint64) * N
+    p = make_params("rate", T0, T0 + 999 * 15_000, 60_000, 300_000)
+    op = orc.make_params("rate", T0, T0 + 999 * 15_000, 60_000, 300_000)
+    e_out, e_valid = orc.range_query(op, ts, val, sid, offsets, threads=8)
+    for use_sid in (True, False):
+        out, valid, ets = ctx.range_eval_n(p, ts, val, sid if use_sid else None, None if use_sid else offsets, S)
+        assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size),
+                     f"pipelined sid={use_sid}")
+    # windows far longer than the ring: every series goes to the slow path and overflows its default arena,
+    # so each chunk is redone alone after the arena has grown
+    p2 = make_params("sum_over_time", T0, T0 + 999 * 15_000, 1_500_000, 6_000_000)
+    op2 = orc.make_params("sum_over_time", T0, T0 + 999 * 15_000, 1_500_000, 6_000_000)
+    e_out, e_valid = orc.range_query(op2, ts, val, sid, offsets, threads=8)
+    out, valid, ets = ctx.range_eval_n(p2, ts, val, sid, None, S)
+    assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size), "pipelined slow path")
+
+
 def test_group_aggregate_matches_oracle(ctx):
     rng = np.random.default_rng(3)
     S, T, G = 700, 77, 13
