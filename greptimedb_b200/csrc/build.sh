@@ -8,5 +8,5 @@ OUT="${HERE}/../libb200promql.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "${NVCC}" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false \
   -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -shared ${B2P_EXTRA_NVCC_FLAGS:-} \
-  -o "${OUT}" "${HERE}/b2p_api.cu"
+  -o "${OUT}" "${HERE}/b2p_api.cu" "${HERE}/b2p_plan.cpp"
 echo "built ${OUT}"

@@ -197,6 +197,55 @@ B2P_API int b2p_histogram_quantile(b2p_ctx* ctx, double phi, const double* le, u
                            const uint32_t* valid_words, uint32_t n_hist, uint64_t T, double* out,
                            uint32_t* out_valid_words);
 
+/* ---- plan-level API over the Arrow C Data Interface ------------------------------------------------
+ * GpuPromRangeExec: the whole sub-tree SeriesDivide -> SeriesNormalize -> RangeManipulate ->
+ * Projection(prom_fn) -> Filter(IS NOT NULL) [-> Aggregate(by-labels, ts).sort()] as one node, fed
+ * with the RecordBatches the scan produces (arrow-rs `arrow::ffi::to_ffi`, pyarrow `_export_to_c`).
+ * Constructor arguments carry the reference's names and meaning (see greptimedb_b200/csrc/b2p_plan.hpp:
+ * SeriesDivide::new series_divide.rs:83-110, SeriesNormalize::new normalize.rs:66-83,
+ * RangeManipulate::new range_manipulate.rs:86-110, UDF names planner.rs:2183-2221).
+ * Input batches must be sorted by (tag columns, time index) — SeriesDivideExec's own requirement.
+ * `function` is the UDF name ("prom_rate", ...); p->fn_id is ignored.  tag columns: Utf8, or a single
+ * UInt64 id column.  aggregate: NULL/"" or "sum|avg|count|min|max|stddev|stdvar" with by_columns ⊆ tags.
+ * b2p_plan_push_batch MOVES the batch (its release callbacks are taken over). b2p_plan_execute
+ * fills caller-provided ArrowArray/ArrowSchema structs; the caller releases them. */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+struct ArrowSchema {
+  const char* format;
+  const char* name;
+  const char* metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema** children;
+  struct ArrowSchema* dictionary;
+  void (*release)(struct ArrowSchema*);
+  void* private_data;
+};
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void** buffers;
+  struct ArrowArray** children;
+  struct ArrowArray* dictionary;
+  void (*release)(struct ArrowArray*);
+  void* private_data;
+};
+#endif
+typedef struct b2p_plan b2p_plan;
+B2P_API b2p_plan* b2p_plan_range_create(b2p_ctx* ctx, const char* function, const b2p_range_params* p,
+                                        const char* time_index, const char* field_column,
+                                        const char* const* tag_columns, int32_t n_tags, const char* aggregate,
+                                        const char* const* by_columns, int32_t n_by);
+B2P_API int b2p_plan_push_batch(b2p_plan* plan, struct ArrowArray* batch, struct ArrowSchema* schema);
+B2P_API int b2p_plan_execute(b2p_plan* plan, struct ArrowArray* out, struct ArrowSchema* out_schema);
+B2P_API int64_t b2p_plan_num_series(b2p_plan* plan);
+B2P_API void b2p_plan_destroy(b2p_plan* plan);
+B2P_API const char* b2p_plan_last_error(void);
+
 /* ---- bench/test utility: synthetic workload generated on the device ------- */
 B2P_API int b2p_synth_fill_dev(b2p_ctx* ctx, uint64_t series_begin, uint64_t n_series, uint32_t n_samples, int64_t t0,
                        int64_t scrape_ms, uint32_t jitter_ms, int32_t with_resets, uint64_t seed, int64_t* ts,
