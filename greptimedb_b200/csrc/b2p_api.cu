@@ -130,7 +130,7 @@ void stage_end(b2p_ctx* c, int stage) {
 
 template <int FN, bool TS32>
 int launch_fast_t(b2p_ctx* c, const RangeArgs& a) {
-  constexpr size_t smem = (size_t)kWarpsPerCta * (kRing * (8 + (TS32 ? 4 : 8)) + kRing / 8) + kRcpTable * 8;
+  constexpr size_t smem = (size_t)kWarpsPerCta * (2 * kRing * (8 + (TS32 ? 4 : 8)) + kRing / 8) + kRcpTable * 8;
   auto kern = range_fast_kernel<FN, kRing, TS32>;
   int& cached = c->fast_blocks_per_sm[FN][TS32 ? 1 : 0];
   if (cached == 0) {

@@ -138,23 +138,25 @@ struct BlockRegs {  // one lane's share (2 rows) of a 64-row block
   bool in0, in1;
 };
 
-__device__ __forceinline__ BlockRegs load_block(const RangeArgs& a, uint64_t blk, uint64_t row0, uint64_t row1,
-                                                int lane) {
+// rel = index (relative to the series' first row, may be -1 for the alignment row) of this lane's first
+// row in the block; n = rows of the series; tail = rows from the series start to the end of the column
+// (saturated to 32 bits).  p_ts / p_val already point at this lane's pair.
+__device__ __forceinline__ BlockRegs load_block(const int64_t* p_ts, const double* p_val, int32_t rel, uint32_t n,
+                                                uint32_t tail) {
   BlockRegs b;
-  const uint64_t r = blk + 2u * (uint64_t)lane;
-  b.in0 = (r >= row0) && (r < row1);
-  b.in1 = (r + 1 >= row0) && (r + 1 < row1);
+  b.in0 = (uint32_t)rel < n;        // unsigned compare also rejects rel == -1
+  b.in1 = (uint32_t)(rel + 1) < n;
   b.t0 = b.t1 = 0;
   b.v0 = b.v1 = 0.0;
   if (b.in0 || b.in1) {
-    if (r + 1 < a.n_rows) {  // both rows inside the allocation: one 128-bit load per column
-      longlong2 tt = __ldcs(reinterpret_cast<const longlong2*>(a.ts + r));
-      double2 vv = __ldcs(reinterpret_cast<const double2*>(a.val + r));
+    if ((uint32_t)(rel + 1) < tail) {  // both rows inside the allocation: one 128-bit load per column
+      const longlong2 tt = __ldcs(reinterpret_cast<const longlong2*>(p_ts));
+      const double2 vv = __ldcs(reinterpret_cast<const double2*>(p_val));
       b.t0 = tt.x; b.t1 = tt.y;
       b.v0 = vv.x; b.v1 = vv.y;
     } else {  // very last row of an odd-length column
-      b.t0 = a.ts[r];
-      b.v0 = a.val[r];
+      b.t0 = p_ts[0];
+      b.v0 = p_val[0];
     }
   }
   return b;
@@ -222,6 +224,7 @@ __device__ __forceinline__ void process_steps(const RangeArgs& a, SeriesState& s
   const time_type te = tlo + rng;
   int32_t hi = st.base_hi;
   uint32_t lo = st.base_lo;
+  acc.set_window((int32_t)st.base_lo - 16);
   if (st.j_cnt > 0) {
     // Window end = last ordinal with ts <= te, window start = first ordinal with ts > te - range.
     // Guess both from the previous group's stride and verify with four predicated ring reads; only when
@@ -341,8 +344,10 @@ __device__ __forceinline__ void process_group_full(const RangeArgs& a, SeriesSta
   uint32_t q;
   time_type t_hi = 0, t_lo = 0;  // ts[g], ts[q] when the guess verified
   bool good;
-  if (st.stride_hi == 1 && st.stride_lo == 1 && st.base_hi >= 0 && st.base_hi + 33 <= top &&
-      (int32_t)st.base_lo + 32 <= top) {
+  acc.set_window((int32_t)st.base_lo - 16);
+  const bool unit_stride = st.stride_hi == 1 && st.stride_lo == 1 && st.base_hi >= 0 && st.base_hi + 33 <= top &&
+                           (int32_t)st.base_lo + 32 <= top;
+  if (unit_stride) {
     g = st.base_hi + 1 + lane;
     q = st.base_lo + 1 + (uint32_t)lane;
     t_hi = acc.t((uint32_t)g);
@@ -367,7 +372,8 @@ __device__ __forceinline__ void process_group_full(const RangeArgs& a, SeriesSta
     t_hi = tg;
     t_lo = tq;
   }
-  if (!__all_sync(0xffffffffu, good)) {  // some guess missed: every lane walks (zero steps where it was right)
+  const bool all_good = __all_sync(0xffffffffu, good);
+  if (!all_good) {  // some guess missed: every lane walks (zero steps where it was right)
     while (g < top && acc.t((uint32_t)(g + 1)) <= te) ++g;
     while (g > st.base_hi && acc.t((uint32_t)g) > te) --g;
     const uint32_t qtop = (uint32_t)(g + 1);
@@ -392,11 +398,18 @@ __device__ __forceinline__ void process_group_full(const RangeArgs& a, SeriesSta
   }
 
   // cursor-overshoot watch (see process_steps)
-  const bool nonempty = l > 0;
-  const uint32_t ne_mask = __ballot_sync(0xffffffffu, nonempty);
   const int32_t nhi = __shfl_sync(0xffffffffu, hi, 31);
   const uint32_t nlo = __shfl_sync(0xffffffffu, lo, 31);
-  if (ne_mask == 0xffffffffu) {
+  const bool nonempty = l > 0;
+  uint32_t ne_mask = 0xffffffffu;
+  if (unit_stride && all_good) {
+    // every window is non-empty, followed by a sample, and starts one ordinal after its predecessor's:
+    // c0 = (lo-1) + 1 = lo < j_cnt for every lane, so only the carried c0 of the previous group can matter
+    if (st.carry_c0 >= st.j_cnt) st.max_c0 = max(st.max_c0, st.carry_c0);
+    st.carry_c0 = nlo;
+    st.lrs = nlo;
+    st.any_nonempty = true;
+  } else if ((ne_mask = __ballot_sync(0xffffffffu, nonempty)) == 0xffffffffu) {
     const bool brk = (hi + 1 < (int32_t)st.j_cnt);
     const uint32_t rsi = (brk && lo > 0) ? lo - 1 : lo;
     uint32_t prev_lo = __shfl_up_sync(0xffffffffu, lo, 1);
@@ -444,14 +457,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_
   constexpr int FW = RING / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // smem: [warps][RING] val f64 | [warps][RING] ts | [kRcpTable] f64 | [warps][FW] flag words
-  double* rval = reinterpret_cast<double*>(smem_raw) + warp * RING;
-  time_type* rts = reinterpret_cast<time_type*>(smem_raw + (size_t)kWarpsPerCta * RING * 8) + warp * RING;
-  double* rcp_tab = reinterpret_cast<double*>(smem_raw + (size_t)kWarpsPerCta * RING * (8 + sizeof(time_type)));
+  // smem: [warps][2*RING] val f64 | [warps][2*RING] ts | [kRcpTable] f64 | [warps][FW] flag words
+  double* rval = reinterpret_cast<double*>(smem_raw) + warp * (2 * RING);
+  time_type* rts = reinterpret_cast<time_type*>(smem_raw + (size_t)kWarpsPerCta * 2 * RING * 8) + warp * (2 * RING);
+  double* rcp_tab = reinterpret_cast<double*>(smem_raw + (size_t)kWarpsPerCta * 2 * RING * (8 + sizeof(time_type)));
   uint32_t* rfl = reinterpret_cast<uint32_t*>(rcp_tab + kRcpTable) + warp * FW;
   for (int i = threadIdx.x; i < kRcpTable; i += blockDim.x) rcp_tab[i] = (i > 0) ? 1.0 / (double)i : 0.0;
   __syncthreads();
-  RingAcc<RING, TS32> acc{rts, rval, rfl, rcp_tab, false};
+  RingAcc<RING, TS32> acc{rts, rval, rfl, rcp_tab, rts, rval, false};
   const uint32_t lt = (1u << lane) - 1u;
   const uint32_t total_warps = gridDim.x * kWarpsPerCta;
   const int32_t T = (int32_t)a.T;
@@ -490,12 +503,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_
       }                                                                                               \
     } while (0)
 
-    uint64_t blk = row0 & ~1ull;  // 16-byte aligned pair boundary
-    BlockRegs nxt = load_block(a, blk, row0, row1, lane);
-    while (blk < row1 && !defer) {
+    // rows are walked in 64-row blocks starting at the 16-byte aligned pair boundary at or before row0;
+    // everything inside the series is 32-bit relative to row0 (a series has < 2^32 rows, like the
+    // reference's RangeTuple = (u32, u32), range_array.rs:24)
+    const uint32_t n_ser = (uint32_t)(row1 - row0);
+    const uint32_t lead = (uint32_t)(row0 & 1ull);
+    const uint64_t tail64 = a.n_rows - row0;
+    const uint32_t tail = tail64 > 0xffffffffull ? 0xffffffffu : (uint32_t)tail64;
+    const int64_t* p_ts = a.ts + (row0 - lead) + 2 * lane;
+    const double* p_val = a.val + (row0 - lead) + 2 * lane;
+    int32_t rel = 2 * lane - (int32_t)lead;    // this lane's first row of the current block, relative to row0
+    const uint32_t n_blk = n_ser + lead;       // rows the blocks have to cover, counted from the aligned start
+    uint32_t done = 0;                         // rows covered by completed blocks
+    BlockRegs nxt = load_block(p_ts, p_val, rel, n_ser, tail);
+    while (done < n_blk && !defer) {
       const BlockRegs cur = nxt;
-      const uint64_t blk_next = blk + 64;
-      if (blk_next < row1) nxt = load_block(a, blk_next, row0, row1, lane);
+      done += 64;
+      const bool more = done < n_blk;
+      if (more) {
+        p_ts += 64;
+        p_val += 64;
+        rel += 64;
+        nxt = load_block(p_ts, p_val, rel, n_ser, tail);
+      }
 
       // ---- SeriesNormalize: drop NaN rows, bias timestamps; append survivors to the ring ----------
       const bool k0 = cur.in0 && !(a.filter_nan && isnan(cur.v0));
@@ -507,15 +537,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_
         const uint32_t j0 = st.j_cnt;
         const uint32_t pos0 = j0 + __popc(b0 & lt) + __popc(b1 & lt);
         const uint32_t pos1 = pos0 + (k0 ? 1u : 0u);
-        if (k0) { rts[pos0 & (RING - 1)] = TD::conv(t0, a); rval[pos0 & (RING - 1)] = cur.v0; }
-        if (k1) { rts[pos1 & (RING - 1)] = TD::conv(t1, a); rval[pos1 & (RING - 1)] = cur.v1; }
+        if (k0) acc.put(pos0, TD::conv(t0, a), cur.v0);
+        if (k1) acc.put(pos1, TD::conv(t1, a), cur.v1);
         st.j_cnt = j0 + __popc(b0) + __popc(b1);
         last_ts = shfl_i64(k1 ? t1 : t0, 31 - __clz(any));
         __syncwarp();
         if constexpr (FnTraits<FN>::kUsesFlags) {
           // Does any new sample reset/change against its predecessor?  Each lane tests its own one or two
           // survivors (predecessor = ring[pos0-1], or its own first sample): one LDS, one ballot.
-          const double prev0 = (pos0 > 0) ? rval[(pos0 - 1) & (RING - 1)] : cur.v0;
+          const double prev0 = (pos0 > 0) ? acc.vm(pos0 - 1) : cur.v0;
           const bool f0 = k0 && pos0 > 0 && flag_pred<FN>(cur.v0, prev0);
           const bool f1 = k1 && pos1 > 0 && flag_pred<FN>(cur.v1, k0 ? cur.v0 : prev0);
           if (__any_sync(0xffffffffu, f0 || f1)) {
@@ -523,7 +553,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_
             for (uint32_t wb = j0 & ~31u; wb < st.j_cnt; wb += 32) {
               const uint32_t j = wb + lane;
               bool f = false;
-              if (j >= 1 && j < st.j_cnt) f = flag_pred<FN>(acc.v(j), acc.v(j - 1));
+              if (j >= 1 && j < st.j_cnt) f = flag_pred<FN>(acc.vm(j), acc.vm(j - 1));
               const uint32_t word = __ballot_sync(0xffffffffu, f);
               if (lane == 0) rfl[(wb >> 5) & (FW - 1)] = word;
               if (word) st.last_flag = wb + 31 - __clz(word);
@@ -558,13 +588,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_
         B2P_RUN_STEPS(k_fin & ~31, T - 1);
       }
       // ---- ring pressure: evaluate what is final, drop samples no future window can reach -----------
-      if (!defer && blk_next < row1 && st.j_cnt + 64u - st.base_lo > (uint32_t)(RING - 32)) {
+      if (!defer && more && st.j_cnt + 64u - st.base_lo > (uint32_t)(RING - 32)) {
         B2P_RUN_STEPS(k_fin, T - 1);  // partial group: frees the ring up to its last window start
         if (!defer) {
           const time_type tlo_next = TD::tlo(a, st.k_next < T ? st.k_next : T - 1);
           while (st.base_lo < st.j_cnt) {
             const uint32_t j = st.base_lo + lane;
-            const bool dead = (j < st.j_cnt) && (acc.t(j) <= tlo_next);
+            const bool dead = (j < st.j_cnt) && (acc.tm(j) <= tlo_next);
             const uint32_t m = __ballot_sync(0xffffffffu, dead);
             const uint32_t adv = (m == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~m) - 1);
             st.base_lo += adv;
@@ -574,7 +604,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_
           if (st.j_cnt + 64u - st.base_lo > (uint32_t)(RING - 32)) defer = true;
         }
       }
-      blk = blk_next;
     }
 
     if (!defer) {

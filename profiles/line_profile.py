@@ -17,7 +17,7 @@ rep, lib, kname, groups = sys.argv[1], sys.argv[2], sys.argv[3], float(sys.argv[
 min_v = float(sys.argv[5]) if len(sys.argv) > 5 else 2.0
 tmp = tempfile.mkdtemp()
 subprocess.run(f"cd {tmp} && cuobjdump -xelf all {os.path.abspath(lib)} >/dev/null 2>&1", shell=True, check=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+cubin = max((f for f in os.listdir(tmp) if f.endswith(".cubin")), key=lambda f: os.path.getsize(os.path.join(tmp, f)))
 sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
 src_csv = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src_csv.splitlines()))

@@ -436,3 +436,76 @@ def test_group_aggregate_matches_oracle(ctx):
         e_out, e_cnt = orc.group_aggregate(op, vals, valid, gid, G)
         assert (g_cnt == e_cnt).all(), op
         assert (g_out.view(np.uint64) == e_out.view(np.uint64)).all(), f"{op}: sequential series order is bit-exact"
+
+
+def test_instant_select_matches_oracle_on_irregular_series(ctx):
+    ts, val, offsets = make_irregular(4242, 80)
+    for (start, end, interval, lookback, offset) in ((1_000_000, 4_000_000, 15_000, 300_000, 0),
+                                                     (999_001, 6_000_000, 60_000, 90_000, 0),
+                                                     (0, 8_000_000, 7_000, 20_000, 123_000),
+                                                     (1_500_000, 1_500_000, 1_000, 300_000, -60_000),
+                                                     (1_000_000, 3_000_000, 5_000, 0, 0)):
+        out, valid = ctx.instant_select(ts, val, start, end, interval, lookback, offset, offsets=offsets)
+        e_out, e_valid = orc.instant_query(ts, val, offsets, start, end, interval, lookback, offset)
+        T = orc.num_steps(start, end, interval)
+        assert_close(out, e_out, orc.valid_to_bool(valid, T), orc.valid_to_bool(e_valid, T),
+                     f"instant lookback={lookback} offset={offset}", bit_exact=True)
+
+
+def test_device_api_sum_by_partials_and_finalize(ctx):
+    """config 3 shape, small: per-shard range_group_sum partials chained into one buffer, then avg finalize."""
+    import torch
+    from greptimedb_b200 import make_params
+    dev = torch.device("cuda:0")
+    S, N, G, T0 = 300, 400, 11, 1_700_000_000_000
+    ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, 1000, 1, 99)
+    offsets = np.arange(S + 1, dtype=np.uint64) * N
+    gid = (np.arange(S) * 7 % G).astype(np.uint32)
+    p = make_params("rate", T0, T0 + (N - 1) * 15_000, 15_000, 300_000)
+    T = N
+    gsum = torch.zeros(G * T, dtype=torch.float64, device=dev)
+    gcnt = torch.zeros(G * T, dtype=torch.int32, device=dev)
+    ctx.use_own_stream()
+    for lo, hi in ((0, 120), (120, 300)):   # two "shards" accumulate into the same partial buffers
+        r0, r1 = lo * N, hi * N
+        d_ts = torch.from_numpy(ts[r0:r1]).to(dev)
+        d_val = torch.from_numpy(val[r0:r1]).to(dev)
+        d_off = torch.from_numpy((offsets[lo:hi + 1] - offsets[lo]).astype(np.int64)).to(dev)
+        d_gid = torch.from_numpy(gid[lo:hi].astype(np.int32)).to(dev)
+        torch.cuda.synchronize()
+        ctx.range_group_sum_dev(p, d_ts, d_val, d_off, r1 - r0, hi - lo, d_gid, G, gsum, gcnt)
+        ctx.sync()
+    ctx.group_finalize_dev("avg", gsum, gcnt, G * T)
+    ctx.sync()
+    op = orc.make_params("rate", T0, T0 + (N - 1) * 15_000, 15_000, 300_000)
+    e_out, e_valid = orc.range_query(op, ts, val, sid, offsets)
+    e_avg, e_cnt = orc.group_aggregate("avg", e_out, e_valid, gid, G)
+    got = gsum.cpu().numpy().reshape(G, T)
+    cnt = gcnt.cpu().numpy().view(np.uint32).reshape(G, T)
+    assert (cnt == e_cnt).all()
+    rel = np.abs(got - e_avg) / np.maximum(np.abs(e_avg), 1e-300)
+    assert rel[e_cnt > 0].max() <= 1e-9
+
+
+def test_column_reduce_config5_shape(ctx):
+    """avg_over_time over a wide table (config 5, small): per-column (sum, count), NaN rows skipped."""
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(11)
+    n_rows, n_cols = 200_003, 32
+    data = rng.normal(size=(n_cols, n_rows)) * 1e3
+    data[rng.random((n_cols, n_rows)) < 0.01] = np.nan
+    cols = [torch.from_numpy(data[c]).to(dev) for c in range(n_cols)]
+    ptrs = torch.tensor([c.data_ptr() for c in cols], dtype=torch.int64, device=dev)
+    out_sum = torch.zeros(n_cols, dtype=torch.float64, device=dev)
+    out_cnt = torch.zeros(n_cols, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    ctx.use_own_stream()
+    for _ in range(2):   # accumulates: two passes double everything
+        ctx.column_reduce_dev(ptrs, n_cols, n_rows, out_sum, out_cnt)
+    ctx.sync()
+    s, c = out_sum.cpu().numpy(), out_cnt.cpu().numpy()
+    assert (c == 2 * (~np.isnan(data)).sum(1)).all()
+    assert np.allclose(s, 2 * np.nansum(data, 1), rtol=1e-11, atol=0)
+    avg = s / c
+    assert np.allclose(avg, np.nanmean(data, 1), rtol=1e-11)
