@@ -31,7 +31,7 @@ if ROOT not in sys.path:
 T0 = 1_700_000_000_000
 N_SAMPLES = 1000
 SCRAPE = 15_000
-RANGE = 300_000
+RANGE = int(os.environ.get("B2P_BENCH_RANGE_MS", "300000"))  # 5m lookback (override: tuning experiments only)
 SEED = 0x5EED
 METRIC = "rate() input samples/sec"
 UNIT = "samples/s"
@@ -197,6 +197,7 @@ def run_ours(args):
         step()
     ctx.sync()
     slow_series = ctx.last_slow_series()
+    warp_tier_series = ctx.last_warp_tier_series()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -294,7 +295,7 @@ def run_ours(args):
                      "traffic": 4.955e9 * (n_rows / 2.0e8), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_k2, "kernel_ms": k2, "k0_series_offsets_ms": k0,
                      "hbm_read_frac_whole_step": read_frac},
-        "gpu_launches": launches, "slow_path_series": slow_series, "clocks": clocks,
+        "gpu_launches": launches, "slow_path_series": slow_series, "warp_tier_series": warp_tier_series, "clocks": clocks,
     }
     if e2e:
         line["e2e"] = e2e

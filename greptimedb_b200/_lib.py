@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("B2P_LIB_PATH") or os.path.join(_HERE, "libb200promql.
 # every symbol include/b200promql.h declares (tests/test_abi.py checks the .so exports them all)
 EXPORTED_SYMBOLS = [
     "b2p_create", "b2p_destroy", "b2p_last_error", "b2p_version", "b2p_set_stream", "b2p_use_own_stream", "b2p_sync", "b2p_num_steps",
-    "b2p_last_slow_series", "b2p_last_kernel_ms", "b2p_launch_count",
+    "b2p_last_slow_series", "b2p_last_warp_tier_series", "b2p_last_kernel_ms", "b2p_launch_count",
     "b2p_series_offsets_dev", "b2p_range_eval_dev", "b2p_range_udf_dev", "b2p_instant_select_dev",
     "b2p_group_aggregate_dev", "b2p_range_group_sum_dev", "b2p_group_finalize_dev", "b2p_histogram_quantile_dev",
     "b2p_column_reduce_dev", "b2p_range_eval", "b2p_range_udf", "b2p_instant_select", "b2p_group_aggregate",
@@ -60,6 +60,7 @@ def load() -> C.CDLL:
         "b2p_sync": (C.c_int, [vp]),
         "b2p_num_steps": (i64, [i64, i64, i64]),
         "b2p_last_slow_series": (i64, [vp]),
+        "b2p_last_warp_tier_series": (i64, [vp]),
         "b2p_last_kernel_ms": (dbl, [vp, C.c_int]),
         "b2p_launch_count": (i64, [vp]),
         "b2p_series_offsets_dev": (C.c_int, [vp, vp, u64, u32, vp]),

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -14,6 +15,7 @@
 
 #include "../../include/b200promql.h"
 #include "b2p_aggregate.cuh"
+#include "b2p_kernel_t.cuh"
 #include "b2p_kernels.cuh"
 
 using namespace b2p;
@@ -81,7 +83,10 @@ struct b2p_ctx {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   Status* d_status = nullptr;
   Status* h_status = nullptr;  // pinned mirror
-  DevBuf slow_list, arena_ts, arena_val, win_scratch;
+  DevBuf slow_list, w_list, arena_ts, arena_val, win_scratch;
+  // K2T (thread per series) in front of K2 for rate/increase/delta.  Measured slower than K2 on B200
+  // (28 vs 64 G samples/s, profiles/r1_thread_tier.md), so it is opt-in: B2P_ENABLE_THREAD_TIER=1.
+  bool thread_tier = false;
   size_t arena_rows = 0;
   cudaEvent_t ev[4][2] = {};
   bool ev_used[4] = {false, false, false, false};
@@ -91,6 +96,7 @@ struct b2p_ctx {
   int last_fn = -1;
   bool pending_range = false;
   long long last_slow = 0;
+  long long last_w = 0;
   // host-API staging
   DevBuf h_ts, h_val, h_sid, h_off, h_out, h_valid, h_aux0, h_aux1, h_aux2, h_aux3;
   // host-API pipeline (double-buffered staging, separate copy streams)
@@ -158,6 +164,18 @@ bool fits_ts32(const RangeArgs& a) {
 template <int FN>
 int launch_fast(b2p_ctx* c, const RangeArgs& a) {
   return fits_ts32(a) ? launch_fast_t<FN, true>(c, a) : launch_fast_t<FN, false>(c, a);
+}
+
+template <int FN>
+int launch_thread_tier(b2p_ctx* c, const RangeArgs& a) {
+  const unsigned batches = (a.n_series + 31) / 32;
+  const unsigned cap = (unsigned)c->num_sms * (unsigned)(220 * 1024 / (kTRing * 32 * 12 + 512));  // shared memory per 1-warp CTA
+  const unsigned grid = batches < cap ? batches : cap;
+  if (grid == 0) return B2P_OK;
+  range_thread_kernel<FN><<<grid, 32, 0, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return B2P_OK;
 }
 
 template <int FN>
@@ -233,6 +251,7 @@ int reset_status(b2p_ctx* c) {
 int ensure_slow_scratch(b2p_ctx* c, uint32_t n_series, int64_t T) {
   int rc;
   if ((rc = c->slow_list.ensure((size_t)(n_series ? n_series : 1) * 4))) return rc;
+  if ((rc = c->w_list.ensure((size_t)(n_series ? n_series : 1) * 4))) return rc;
   if ((rc = c->win_scratch.ensure((size_t)kSlowWarps * (size_t)(T > 0 ? T : 1) * 8))) return rc;
   if (c->arena_rows == 0) {
     if ((rc = c->arena_ts.ensure(kArenaDefaultRows * 8))) return rc;
@@ -287,6 +306,17 @@ b2p_ctx* b2p_create(int device) {
     return nullptr;
   }
   cudaMemset(c->d_status, 0, sizeof(Status));
+  {
+    double tab[kRcpTable];
+    tab[0] = 0.0;
+    for (int i = 1; i < kRcpTable; ++i) tab[i] = 1.0 / (double)i;
+    if (cudaMemcpyToSymbol(c_rcp_table, tab, sizeof tab) != cudaSuccess) {
+      fail(B2P_E_CUDA, "constant table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+      b2p_destroy(c);
+      return nullptr;
+    }
+  }
+  if (const char* e = getenv("B2P_ENABLE_THREAD_TIER")) c->thread_tier = (e[0] == '1');
   return c;
 }
 
@@ -294,7 +324,7 @@ void b2p_destroy(b2p_ctx* c) {
   if (!c) return;
   DeviceGuard g(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-  for (DevBuf* b : {&c->slow_list, &c->arena_ts, &c->arena_val, &c->win_scratch, &c->h_ts, &c->h_val, &c->h_sid,
+  for (DevBuf* b : {&c->slow_list, &c->w_list, &c->arena_ts, &c->arena_val, &c->win_scratch, &c->h_ts, &c->h_val, &c->h_sid,
                     &c->h_off, &c->h_out, &c->h_valid, &c->h_aux0, &c->h_aux1, &c->h_aux2, &c->h_aux3,
                     &c->g_keys_in, &c->g_keys_out, &c->g_vals_in, &c->g_vals_out, &c->g_goff, &c->g_tmp, &c->c_psum,
                     &c->c_pcnt})
@@ -330,6 +360,7 @@ int b2p_use_own_stream(b2p_ctx* c) {
 }
 
 int64_t b2p_last_slow_series(b2p_ctx* c) { return c ? c->last_slow : -1; }
+int64_t b2p_last_warp_tier_series(b2p_ctx* c) { return c ? c->last_w : -1; }
 int64_t b2p_launch_count(b2p_ctx* c) { return c ? c->launches : -1; }
 
 double b2p_last_kernel_ms(b2p_ctx* c, int stage) {
@@ -351,6 +382,7 @@ int b2p_sync(b2p_ctx* c) {
     CU(cudaStreamSynchronize(c->stream));
     const Status st = *c->h_status;
     c->last_slow = st.slow_count;
+    c->last_w = st.w_count;
     if (st.k0_errors & 1u) return fail(B2P_E_UNSORTED, "series-id column is not non-decreasing");
     if (st.k0_errors & 2u) return fail(B2P_E_UNSORTED, "series id >= n_series");
     if (!st.arena_overflow) {
@@ -433,16 +465,31 @@ int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts,
     const bool all_ones = (bits & 0x000fffffffffffffull) == 0x000fffffffffffffull;
     a.rcp_rs = (p->range > 0 && !all_ones) ? 1.0 / rs : 0.0;
     a.range_secs = rs;
+    a.rcp_interval = 1.0 / (double)p->interval;
   }
   a.ts = ts; a.val = val; a.offsets = offsets; a.n_rows = n_rows; a.n_series = n_series;
   a.out = out; a.valid = valid_words;
   a.status = c->d_status; a.slow_list = c->slow_list.as<uint32_t>();
+  a.w_list = c->w_list.as<uint32_t>();
+  a.use_w_list = 0;
   a.arena_ts = c->arena_ts.as<int64_t>(); a.arena_val = c->arena_val.as<double>(); a.arena_cap = c->arena_rows;
   a.win_scratch = c->win_scratch.as<unsigned long long>();
   // the status block also carries K0's verdict; only the slow-path fields are reset here
   CU(cudaMemsetAsync(&c->d_status->slow_count, 0, 2 * sizeof(uint32_t), c->stream));
+  CU(cudaMemsetAsync(&c->d_status->w_count, 0, sizeof(uint32_t), c->stream));
   CU(cudaMemsetAsync(&c->d_status->arena_used, 0, 2 * sizeof(unsigned long long), c->stream));
   stage_begin(c, 1);
+  // tier 1 (rate / increase / delta, 32-bit time domain): thread per series; what it declines goes to
+  // tier 2 (warp per series) through w_list, and what that declines to the exact slow kernel
+  const bool tier1 = c->thread_tier && fits_ts32(a) &&
+                     (p->fn_id == B2P_FN_RATE || p->fn_id == B2P_FN_INCREASE || p->fn_id == B2P_FN_DELTA);
+  if (tier1) {
+    if (p->fn_id == B2P_FN_RATE) rc = launch_thread_tier<B2P_FN_RATE>(c, a);
+    else if (p->fn_id == B2P_FN_INCREASE) rc = launch_thread_tier<B2P_FN_INCREASE>(c, a);
+    else rc = launch_thread_tier<B2P_FN_DELTA>(c, a);
+    if (rc) return rc;
+    a.use_w_list = 1;
+  }
   rc = dispatch_fast(c, p->fn_id, a);
   stage_end(c, 1);
   if (rc) return rc;

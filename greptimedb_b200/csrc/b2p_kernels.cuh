@@ -29,7 +29,7 @@ struct Status {
   uint32_t slow_count;      // series deferred to the slow path          (reset per range call)
   uint32_t arena_overflow;  // slow-path arena too small                 (reset per range call)
   uint32_t k0_errors;       // bit0: sid not sorted, bit1: sid >= n_series (reset per K0 call)
-  uint32_t pad;
+  uint32_t w_count;         // series the thread-per-series tier handed to the warp-per-series kernel
   unsigned long long arena_used;    // rows claimed in the slow-path arena
   unsigned long long arena_needed;  // rows that would have been needed
 };
@@ -46,6 +46,7 @@ struct RangeArgs {
   uint32_t rel_max;  // range + (T-1)*interval + 1: clamp for samples after `end`
   double rcp_rs;     // RN(1/(range/1000)) when the Markstein division is exact for it, else 0
   double range_secs; // (double)range / 1000.0
+  double rcp_interval; // 1.0 / interval
   // input
   const int64_t* ts;
   const double* val;
@@ -55,6 +56,9 @@ struct RangeArgs {
   // output
   double* out;
   uint32_t* valid;
+  // tier hand-off: when use_w_list != 0 the warp-per-series kernel only runs the series in w_list
+  uint32_t* w_list;
+  int32_t use_w_list;
   // slow path plumbing
   Status* status;
   uint32_t* slow_list;
@@ -469,7 +473,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_
   const uint32_t total_warps = gridDim.x * kWarpsPerCta;
   const int32_t T = (int32_t)a.T;
 
-  for (uint32_t s = blockIdx.x * kWarpsPerCta + warp; s < a.n_series; s += total_warps) {
+  const uint32_t n_work = a.use_w_list ? a.status->w_count : a.n_series;
+  for (uint32_t wi = blockIdx.x * kWarpsPerCta + warp; wi < n_work; wi += total_warps) {
+    const uint32_t s = a.use_w_list ? a.w_list[wi] : wi;
     const uint64_t row0 = a.offsets[s], row1 = a.offsets[s + 1];
     double* const out_s = a.out + (size_t)s * (size_t)T;
     uint32_t* const vw_s = a.valid + (size_t)s * a.Tw;
@@ -562,7 +568,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_
             // no set bit among the new ordinals: clear the words they start (a partially filled word
             // already holds zeros above the previous j_cnt)
             const uint32_t w_first = (j0 + 31) >> 5, w_last = (st.j_cnt - 1) >> 5;
-            if (w_first + (uint32_t)lane <= w_last) rfl[(w_first + lane) & (FW - 1)] = 0u;
+            if (lane < 3 && w_first + (uint32_t)lane <= w_last) rfl[(w_first + lane) & (FW - 1)] = 0u;
           }
           __syncwarp();
         }
@@ -577,8 +583,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_
         // steps whose window can no longer change and that the end-trim cannot remove:
         // t_k <= ts_cur - interval  <=>  k < floor((ts_cur - start) / interval)
         if constexpr (TS32) {
+          // floor((rel - range) / interval) by reciprocal multiply + one correction step (exact for the
+          // < 2^31 operands of the 32-bit time domain: the double product is within 1 of the quotient)
           const uint32_t rel = TD::conv(last_ts, a);
-          k_fin = rel >= (uint32_t)a.range ? (int32_t)((rel - (uint32_t)a.range) / (uint32_t)a.interval) : 0;
+          if (rel >= (uint32_t)a.range) {
+            const uint32_t x = rel - (uint32_t)a.range, d = (uint32_t)a.interval;
+            uint32_t q = (uint32_t)__double2uint_rz((double)x * a.rcp_interval);
+            const uint32_t back = q * d;
+            if (back > x) --q; else if (x - back >= d) ++q;
+            k_fin = (int32_t)q;
+          } else {
+            k_fin = 0;
+          }
         } else {
           const int64_t kk = floor_div(last_ts - a.start, a.interval);
           k_fin = kk < 0 ? 0 : (kk > (int64_t)T ? T : (int32_t)kk);

@@ -133,6 +133,8 @@ B2P_API int b2p_sync(b2p_ctx* ctx);
 B2P_API int64_t b2p_num_steps(int64_t start, int64_t end, int64_t interval);
 /* Series the last range/instant call routed to the exact slow path (diagnostic; after b2p_sync). */
 B2P_API int64_t b2p_last_slow_series(b2p_ctx* ctx);
+/* Series the thread-per-series tier handed to the warp-per-series kernel in the last call (diagnostic). */
+B2P_API int64_t b2p_last_warp_tier_series(b2p_ctx* ctx);
 /* CUDA-event time (ms) of the kernels of the last *_dev / host call, by stage index:
  * 0 = series_offsets, 1 = range/instant fast kernel, 2 = slow-path kernel, 3 = aggregate /
  * histogram / reduce kernel.  Valid after b2p_sync(). */

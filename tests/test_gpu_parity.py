@@ -301,16 +301,33 @@ def test_int64_ring_path_on_spans_over_24_days(ctx):
                      f"ts64 {fn}", bit_exact=fn in BIT_EXACT)
 
 
-def test_rate_is_bit_exact_against_the_rescan_oracle(ctx):
-    """The two-FMA divisions (by window length, by range seconds) must round exactly like IEEE division."""
+@pytest.fixture(scope="module")
+def ctx_thread_tier():
+    """A context with the opt-in thread-per-series tier (K2T) switched on for rate / increase / delta."""
+    import os
+    from greptimedb_b200 import Context
+    os.environ["B2P_ENABLE_THREAD_TIER"] = "1"
+    try:
+        c = Context(0)
+    finally:
+        del os.environ["B2P_ENABLE_THREAD_TIER"]
+    yield c
+    c.close()
+
+
+RATE_EXACT_SHAPES = ((1000, 1, 300_000), (0, 0, 300_000), (977, 1, 77_777), (1000, 0, 1_000_000))
+
+
+def test_rate_warp_tier_is_bit_exact_against_the_rescan_oracle(ctx):
+    """Warp-per-series kernel: the two-FMA divisions (by window length, by range seconds) must round exactly
+    like IEEE division, and the bitmask reset correction must add exactly what the reference's rescan adds."""
     from greptimedb_b200 import make_params
     S, N, T0 = 256, 1000, 1_700_000_000_000
-    for jitter, resets, rng_ms in ((1000, 1, 300_000), (0, 0, 300_000), (977, 1, 77_777), (1000, 0, 1_000_000)):
+    for jitter, resets, rng_ms in RATE_EXACT_SHAPES:
         ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, jitter, resets, 0x5EED)
         p = make_params("rate", T0, T0 + 999 * 15_000, 15_000, rng_ms)
         out, valid, ets = ctx.range_eval_n(p, ts, val, sid, None, S)
         vb = orc.valid_to_bool(valid, ets.size)
-        # oracle, rescan variant, window by window
         for s in range(0, S, 37):
             o = s * N
             off, ln, s2, e2 = orc.calculate_range(ts[o:o + N], T0, T0 + 999 * 15_000, 15_000, rng_ms)
@@ -320,6 +337,43 @@ def test_rate_is_bit_exact_against_the_rescan_oracle(ctx):
             got = out[s, k0:k0 + e.size]
             assert (vb[s, k0:k0 + e.size] == ev).all()
             assert (got.view(np.uint64)[ev] == e.view(np.uint64)[ev]).all(), (jitter, resets, rng_ms, s)
+
+
+def test_rate_thread_tier_is_bit_exact_against_the_reference_sliding_path(ctx_thread_tier):
+    ctx = ctx_thread_tier
+    """Thread-per-series kernel: visits the steps in order and maintains counter_correction exactly like
+    ExtrapolatedRate::calc (slide when the window slides by one sample, rescan otherwise), so whole series must be
+    bit-identical to the oracle's default (sliding) restatement — for rate, increase and delta."""
+    from greptimedb_b200 import make_params
+    S, N, T0 = 256, 1000, 1_700_000_000_000
+    offsets = np.arange(S + 1, dtype=np.uint64) * N
+    for fn in ("rate", "increase", "delta"):
+        for jitter, resets, rng_ms in RATE_EXACT_SHAPES:
+            ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, jitter, resets, 0x5EED)
+            for interval in (15_000, 45_000, 7_000):
+                p = make_params(fn, T0 + 5, T0 + 999 * 15_000 + 40_000, interval, rng_ms)
+                out, valid, ets = ctx.range_eval_n(p, ts, val, sid, None, S)
+                op = orc.make_params(fn, T0 + 5, T0 + 999 * 15_000 + 40_000, interval, rng_ms)
+                e_out, e_valid = orc.range_query(op, ts, val, sid, offsets, threads=4)
+                assert (valid == e_valid).all(), (fn, jitter, resets, rng_ms, interval)
+                assert (out.view(np.uint64) == e_out.view(np.uint64)).all(), (fn, jitter, resets, rng_ms, interval)
+                assert ctx.last_slow_series() == 0
+
+
+def test_thread_tier_hands_off_what_it_cannot_do(ctx_thread_tier):
+    """NaN series, long windows, the overshoot quirk and dense bursts leave K2T for K2 / the slow kernel; results
+    still match the oracle on the irregular suite."""
+    from greptimedb_b200 import make_params
+    ts, val, offsets = make_irregular(1234, 96)
+    for fn in ("rate", "increase", "delta"):
+        for qi, q in enumerate(QUERY_SHAPES):
+            p = make_params(fn, q["start"], q["end"], q["interval"], q["range"], offset=q["offset"])
+            out, valid, ets = ctx_thread_tier.range_eval(p, ts, val, offsets=offsets)
+            op = orc.make_params(fn, q["start"], q["end"], q["interval"], q["range"], offset=q["offset"])
+            e_out, e_valid = orc.range_query(op, ts, val, None, offsets)
+            assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size),
+                         f"thread tier {fn} shape {qi}")
+    assert ctx_thread_tier.last_warp_tier_series() > 0
 
 
 def test_nan_filter_off_passes_nan_through(ctx):
