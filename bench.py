@@ -183,9 +183,25 @@ def run_ours(args):
     ctx.sync()
     torch.cuda.synchronize()
 
+    sumby = args.workload == "sumby"
+    if sumby:
+        # BASELINE config 3: sum by (pod)(rate(x[5m])), 100 k label groups over the whole 10 M-series job;
+        # every rank reduces its shard into [G x T] (sum, cnt) partials, ONE all-reduce per buffer merges them
+        from greptimedb_b200 import distributed as D
+        G = args.groups
+        gid_np = (D.mix32(np.arange(rank * S, (rank + 1) * S, dtype=np.uint32)) % np.uint32(G)).astype(np.int32)
+        gid = torch.from_numpy(gid_np).to(dev)
+        gsum = torch.zeros(G * T, dtype=torch.float64, device=dev)
+        gcnt = torch.zeros(G * T, dtype=torch.int32, device=dev)
+
     def step():
         ctx.series_offsets_dev(sid, n_rows, S, offsets)
         ctx.range_eval_dev(p, ts, val, offsets, n_rows, S, out, valid)
+        if sumby:
+            ctx.group_aggregate_dev("sum", out, valid, gid, S, G, T, gsum, gcnt)
+            if world > 1:
+                dist.all_reduce(gsum)
+                dist.all_reduce(gcnt)
 
     def barrier():
         torch.cuda.synchronize()
@@ -283,10 +299,12 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"rate(x[5m]) step 15s over {S} series x {N_SAMPLES} samples per GPU per step "
+        "config": {"workload": (f"sum by(pod)(rate(x[5m])) -> {args.groups} groups + all-reduce, " if sumby else "") +
+                               f"rate(x[5m]) step 15s over {S} series x {N_SAMPLES} samples per GPU per step "
                                f"(BASELINE config 2 = 10M series processed as chunks of {S}); resets={args.resets}",
                    "series_per_gpu_per_step": S, "samples_per_series": N_SAMPLES, "eval_steps": T,
-                   "parallelism": f"series-sharded x{world}, no data-path collective",
+                   "parallelism": f"series-sharded x{world}, " + ("one all-reduce of [G x T] (sum f64, cnt i32) per step"
+                                                                  if sumby else "no data-path collective"),
                    "l2": "inputs (16-25 GB per step) >> 126 MB L2; no flush needed"},
         "roofline": {"bound": "hbm", "kernel": "range_fast_kernel<rate>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
@@ -322,6 +340,9 @@ def main():
     ap.add_argument("--e2e-series", type=int, default=131_072)
     ap.add_argument("--resets", type=int, default=0, help="1 = counter-reset variant of the value generator")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="rate", choices=["rate", "sumby"],
+                    help="rate = BASELINE config 2 (headline); sumby = config 3: + by-label sum and one all-reduce")
+    ap.add_argument("--groups", type=int, default=100_000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
