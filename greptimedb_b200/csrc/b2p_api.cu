@@ -425,7 +425,7 @@ static int series_offsets_impl(b2p_ctx* c, const uint32_t* sid, uint64_t n_rows,
   if (!c || !offsets || (!sid && n_rows)) return fail(B2P_E_INVALID, "NULL argument");
   if (!aligned16(sid)) return fail(B2P_E_INVALID, "sid must be 16-byte aligned");
   DeviceGuard g(c->device);
-  uint64_t blocks = (n_rows / 4 + 255) / 256;
+  uint64_t blocks = (n_rows / 8 + 255) / 256;
   const uint64_t cap = (uint64_t)c->num_sms * 16;
   if (blocks > cap) blocks = cap;
   if (blocks == 0) blocks = 1;

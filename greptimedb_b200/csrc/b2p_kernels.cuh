@@ -82,40 +82,58 @@ __device__ __forceinline__ int64_t rem_euclid(int64_t a, int64_t b) {
 // Replaces find_first_diff_row's row-by-row tag compare (series_divide.rs:622-670); ids must be
 // non-decreasing (the reference requires the same ordering, series_divide.rs:410-440).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void offsets_scan(const uint32_t* v, int cnt, uint32_t prev, uint64_t r0, uint64_t n_rows,
+                                             uint32_t n_series, uint64_t* __restrict__ offsets, Status* status) {
+  for (int i = 0; i < cnt; ++i) {
+    const uint64_t r = r0 + i;
+    const uint32_t cur = v[i];
+    if (cur >= n_series) {
+      atomicOr(&status->k0_errors, 2u);
+    } else if (r == 0) {
+      for (uint32_t s = 0; s <= cur; ++s) offsets[s] = 0;
+    } else if (cur != prev) {
+      if (cur < prev)
+        atomicOr(&status->k0_errors, 1u);
+      else
+        for (uint32_t s = prev + 1; s <= cur; ++s) offsets[s] = r;
+    }
+    if (r == n_rows - 1 && cur < n_series)
+      for (uint32_t s = cur + 1; s <= n_series; ++s) offsets[s] = n_rows;
+    prev = cur;
+  }
+}
+
 __global__ void __launch_bounds__(256) series_offsets_kernel(const uint32_t* __restrict__ sid, uint64_t n_rows,
                                                              uint32_t n_series, uint32_t sid_base,
                                                              uint64_t* __restrict__ offsets, Status* status) {
-  const uint64_t n4 = (n_rows + 3) / 4;
-  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t r0 = q * 4;
-    uint32_t v[4];
-    if (r0 + 3 < n_rows) {
-      uint4 x = __ldcs(reinterpret_cast<const uint4*>(sid + r0));
-      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  // 8 ids per thread per iteration (two independent 128-bit loads in flight).  Almost every octet lies
+  // inside one series: a branch-free XOR/OR test against the preceding id skips it; only octets
+  // that contain a change (or the first / last row) take the scalar scan.
+  const uint64_t n8 = (n_rows + 7) / 8;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n8; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r0 = q * 8;
+    uint32_t v[8];
+    int cnt = 8;
+    if (r0 + 7 < n_rows) {
+      const uint4 x0 = __ldcs(reinterpret_cast<const uint4*>(sid + r0));
+      const uint4 x1 = __ldcs(reinterpret_cast<const uint4*>(sid + r0 + 4));
+      v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
+      v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
     } else {
+      cnt = (int)(n_rows - r0);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = (r0 + i < n_rows) ? sid[r0 + i] : 0u;
+      for (int i = 0; i < 8; ++i) v[i] = (i < cnt) ? sid[r0 + i] : 0u;
     }
-    uint32_t prev = (r0 == 0) ? 0u : sid[r0 - 1] - sid_base;
+    const uint32_t prev_raw = (r0 == 0) ? v[0] : sid[r0 - 1];
+    uint32_t diff = prev_raw ^ v[0];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint64_t r = r0 + i;
-      if (r >= n_rows) break;
-      const uint32_t cur = v[i] - sid_base;  // ids below sid_base wrap to >= n_series and are flagged
-      if (cur >= n_series) {
-        atomicOr(&status->k0_errors, 2u);
-      } else if (r == 0) {
-        for (uint32_t s = 0; s <= cur; ++s) offsets[s] = 0;
-      } else if (cur != prev) {
-        if (cur < prev)
-          atomicOr(&status->k0_errors, 1u);
-        else
-          for (uint32_t s = prev + 1; s <= cur; ++s) offsets[s] = r;
-      }
-      if (r == n_rows - 1 && cur < n_series)
-        for (uint32_t s = cur + 1; s <= n_series; ++s) offsets[s] = n_rows;
-      prev = cur;
-    }
+    for (int i = 1; i < 8; ++i) diff |= (i < cnt) ? (v[i - 1] ^ v[i]) : 0u;
+    const bool edge = (r0 == 0) || (r0 + 8 >= n_rows);
+    const bool in_range = (v[0] - sid_base) < n_series;  // no change => one check covers the octet
+    if (diff == 0u && !edge && in_range) continue;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] -= sid_base;  // ids below sid_base wrap to >= n_series and are flagged
+    offsets_scan(v, cnt, prev_raw - sid_base, r0, n_rows, n_series, offsets, status);
   }
   if (n_rows == 0 && blockIdx.x == 0)
     for (uint32_t s = threadIdx.x; s <= n_series; s += blockDim.x) offsets[s] = 0;
