@@ -309,8 +309,8 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "range_fast_kernel<rate>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
-                     # capture (profiles/r1_range_fast_kernel.md, 2e8-sample launch: 4.955 GB), scaled to this launch
-                     "traffic": 4.955e9 * (n_rows / 2.0e8), "peak_source": peak_src,
+                     # capture (profiles/r1_range_fast_kernel.md, version f, 2e8-sample launch: 3.381 + 1.585 GB), scaled
+                     "traffic": 4.966e9 * (n_rows / 2.0e8), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_k2, "kernel_ms": k2, "k0_series_offsets_ms": k0,
                      "hbm_read_frac_whole_step": read_frac},
         "gpu_launches": launches, "slow_path_series": slow_series, "warp_tier_series": warp_tier_series, "clocks": clocks,

@@ -19,7 +19,11 @@ tmp = tempfile.mkdtemp()
 subprocess.run(f"cd {tmp} && cuobjdump -xelf all {os.path.abspath(lib)} >/dev/null 2>&1", shell=True, check=True)
 cubin = max((f for f in os.listdir(tmp) if f.endswith(".cubin")), key=lambda f: os.path.getsize(os.path.join(tmp, f)))
 sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
-src_csv = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+short = re.sub(r"^_ZN\d+[a-z0-9]+?(\d+)", "", kname)
+m_ = re.match(r"_ZN3b2p(\d+)", kname)
+fname = kname[len(m_.group(0)):len(m_.group(0)) + int(m_.group(1))] if m_ else kname
+src_csv = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + fname],
+                         capture_output=True, text=True).stdout
 rows = list(csv.reader(src_csv.splitlines()))
 hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
 hdr = rows[hi]
