@@ -46,8 +46,12 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+
+    The sampler is started before the warm-up (nvidia-smi takes a few hundred ms to produce its first line) and
+    every line carries a timestamp; stop(t0, t1) keeps the samples that fall inside the timed window [t0, t1]
+    (wall clock), or — if the window was shorter than the sampling period — the samples nearest to it."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -59,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -68,31 +72,48 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        rows = []
+        for seen, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
+            if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                import datetime
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                ts = seen
+            try:
+                rows.append((ts, float(f[2]), float(f[3]), f[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        where = "inside the timed region"
+        if not inside and rows and t0 is not None:
+            mid = 0.5 * (t0 + t1)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            where = "nearest to the timed region (region shorter than the sampling period)"
+        if t0 is None:
+            inside = rows
+        sm = [r[1] for r in inside]
+        mx = [r[2] for r in inside]
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": where}
 
 
 def query_params():
@@ -209,16 +230,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     ctx.sync()
     slow_series = ctx.last_slow_series()
     warp_tier_series = ctx.last_warp_tier_series()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = ctx.launch_count()
+    wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0_ms, k2_ms = [], []
     ev0.record()
@@ -227,9 +249,10 @@ def run_ours(args):
     ev1.record()
     ctx.sync()
     barrier()
+    wall1 = time.time()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     # per-kernel durations: re-run K untimed-by-the-headline steps reading the library's own CUDA events
     for _ in range(min(args.steps, 5)):
         step()
