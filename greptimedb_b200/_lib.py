@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "b2p_group_aggregate_dev", "b2p_range_group_sum_dev", "b2p_group_finalize_dev", "b2p_histogram_quantile_dev",
     "b2p_column_reduce_dev", "b2p_range_eval", "b2p_range_udf", "b2p_instant_select", "b2p_group_aggregate",
     "b2p_histogram_quantile", "b2p_synth_fill_dev",
-    "b2p_plan_range_create", "b2p_plan_push_batch", "b2p_plan_execute", "b2p_plan_num_series", "b2p_plan_destroy",
+    "b2p_plan_range_create", "b2p_plan_set_instant", "b2p_plan_set_histogram_quantile", "b2p_plan_push_batch", "b2p_plan_execute", "b2p_plan_num_series", "b2p_plan_destroy",
     "b2p_plan_last_error",
 ]
 
@@ -80,6 +80,8 @@ def load() -> C.CDLL:
         "b2p_synth_fill_dev": (C.c_int, [vp, u64, u64, u32, i64, i64, u32, i32, u64, vp, vp, vp]),
         "b2p_plan_range_create": (vp, [vp, C.c_char_p, P, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), i32, C.c_char_p,
                                        C.POINTER(C.c_char_p), i32]),
+        "b2p_plan_set_instant": (C.c_int, [vp, i64]),
+        "b2p_plan_set_histogram_quantile": (C.c_int, [vp, C.c_char_p, dbl]),
         "b2p_plan_push_batch": (C.c_int, [vp, vp, vp]),
         "b2p_plan_execute": (C.c_int, [vp, vp, vp]),
         "b2p_plan_num_series": (i64, [vp]),

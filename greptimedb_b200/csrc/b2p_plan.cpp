@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <numeric>
 
@@ -109,8 +110,15 @@ int RecordBatch::find(const std::string& name) const {
 // ---- PromRangePlan -------------------------------------------------------------------------------------
 PromRangePlan::PromRangePlan(b2p_ctx* ctx, PromRangePlanArgs args) : ctx_(ctx), args_(std::move(args)) {
   if (!ctx_) throw PlanError(ErrorKind::Internal, "GpuPromRangeExec: NULL context");
-  fn_id_ = function_id_from_name(args_.function);
-  if (fn_id_ < 0) throw PlanError(ErrorKind::Plan, "GpuPromRangeExec: unknown range function " + args_.function);
+  fn_id_ = args_.function.empty() ? -1 : function_id_from_name(args_.function);
+  if (fn_id_ < 0 && !args_.function.empty())
+    throw PlanError(ErrorKind::Plan, "GpuPromRangeExec: unknown range function " + args_.function);
+  if (args_.histogram) {
+    if (std::find(args_.tag_columns.begin(), args_.tag_columns.end(), args_.le_column) == args_.tag_columns.end())
+      throw PlanError(ErrorKind::Plan, "HistogramFold: le column " + args_.le_column + " is not a tag column");
+    if (!args_.aggregate.empty())
+      throw PlanError(ErrorKind::Plan, "HistogramFold over an aggregate is not supported by this node");
+  }
   agg_id_ = -1;
   if (!args_.aggregate.empty()) {
     agg_id_ = aggregate_id_from_name(args_.aggregate);
@@ -123,6 +131,16 @@ PromRangePlan::PromRangePlan(b2p_ctx* ctx, PromRangePlanArgs args) : ctx_(ctx), 
   if (args_.time_index.empty() || args_.field_column.empty())
     throw PlanError(ErrorKind::Plan, "GpuPromRangeExec: time index and field column are required");
   tags_.utf8.resize(args_.tag_columns.size());
+}
+
+void PromRangePlan::set_histogram(const std::string& le_column, double quantile) {
+  if (std::find(args_.tag_columns.begin(), args_.tag_columns.end(), le_column) == args_.tag_columns.end())
+    throw PlanError(ErrorKind::Plan, "HistogramFold: le column " + le_column + " is not a tag column");
+  if (!args_.aggregate.empty())
+    throw PlanError(ErrorKind::Plan, "HistogramFold over an aggregate is not supported by this node");
+  args_.histogram = true;
+  args_.le_column = le_column;
+  args_.quantile = quantile;
 }
 
 void PromRangePlan::push(std::unique_ptr<RecordBatch> batch) {
@@ -243,12 +261,21 @@ void PromRangePlan::execute(ArrowArray* out, ArrowSchema* out_schema) {
   std::vector<uint32_t> valid((size_t)S * Tw);
   std::vector<int64_t> eval_ts((size_t)T);
   if (S > 0 && T > 0) {
-    const int rc = b2p_range_eval(ctx_, &p, ts_.data(), val_.data(), sid_.data(), nullptr, ts_.size(), S, dense.data(),
-                                  valid.data(), eval_ts.data());
+    int rc;
+    if (fn_id_ >= 0) {
+      rc = b2p_range_eval(ctx_, &p, ts_.data(), val_.data(), sid_.data(), nullptr, ts_.size(), S, dense.data(),
+                          valid.data(), eval_ts.data());
+    } else {  // InstantManipulate
+      rc = b2p_instant_select(ctx_, p.start, p.end, p.interval, args_.lookback_delta, p.offset, ts_.data(),
+                              val_.data(), sid_.data(), nullptr, ts_.size(), S, dense.data(), valid.data());
+      for (int64_t k = 0; k < T; ++k) eval_ts[(size_t)k] = p.start + k * p.interval;
+    }
     if (rc == B2P_E_INVALID || rc == B2P_E_TOO_LARGE) throw PlanError(ErrorKind::Plan, b2p_last_error());
     if (rc == B2P_E_UNSORTED) throw PlanError(ErrorKind::Internal, b2p_last_error());
     if (rc != B2P_OK) throw PlanError(ErrorKind::Execution, b2p_last_error());
   }
+  const std::string value_name =
+      fn_id_ >= 0 ? args_.function + "(" + args_.time_index + "_range," + args_.field_column + ")" : args_.field_column;
 
   auto ob = std::make_unique<OwnedBatch>();
   auto os = std::make_unique<OwnedSchema>();
@@ -260,10 +287,81 @@ void PromRangePlan::execute(ArrowArray* out, ArrowSchema* out_schema) {
   };
   int64_t n_out = 0;
 
-  if (agg_id_ < 0) {
+  if (args_.histogram) {
+    // HistogramFold (histogram_fold.rs:754-820): group the series by their tags without `le`, order each group's
+    // buckets by le ascending (parsed as f64, "+Inf" last), one output row per (group, eval ts)
+    if (key_is_id_) throw PlanError(ErrorKind::Plan, "HistogramFold needs the le tag column, not a tsid key");
+    const size_t le_idx = (size_t)(std::find(args_.tag_columns.begin(), args_.tag_columns.end(), args_.le_column) -
+                                   args_.tag_columns.begin());
+    std::map<std::vector<std::string>, std::vector<std::pair<double, uint32_t>>> hist;  // key -> (le, series)
+    for (uint32_t s = 0; s < S; ++s) {
+      std::vector<std::string> key;
+      for (size_t t = 0; t < args_.tag_columns.size(); ++t)
+        if (t != le_idx) key.push_back(tags_.utf8[t][s]);
+      const std::string& le_s = tags_.utf8[le_idx][s];
+      char* endp = nullptr;
+      double le = std::strtod(le_s.c_str(), &endp);  // le.parse::<f64>().unwrap_or(NaN), histogram_fold.rs:791-796
+      if (endp == le_s.c_str() || *endp != 0) le = std::nan("");
+      hist[key].push_back({le, s});
+    }
+    std::vector<double> le_bounds;
+    std::vector<uint32_t> order;  // series in (histogram, bucket) order
+    for (auto& kv : hist) {
+      auto& b = kv.second;
+      std::stable_sort(b.begin(), b.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+      if (le_bounds.empty()) {
+        for (auto& e : b) le_bounds.push_back(e.first);
+      } else {
+        bool same = b.size() == le_bounds.size();
+        for (size_t i = 0; same && i < b.size(); ++i)
+          same = (b[i].first == le_bounds[i]) || (std::isnan(b[i].first) && std::isnan(le_bounds[i]));
+        if (!same)
+          throw PlanError(ErrorKind::Execution, "HistogramFold: histograms with different bucket layouts (the reference's "
+                                                "safe mode, histogram_fold.rs:834-846) are not supported by the GPU node");
+      }
+      for (auto& e : b) order.push_back(e.second);
+    }
+    const uint32_t B = (uint32_t)le_bounds.size();
+    const uint32_t H = (uint32_t)hist.size();
+    std::vector<double> hr((size_t)H * B * (size_t)T);
+    std::vector<uint32_t> hv((size_t)H * B * Tw);
+    for (size_t i = 0; i < order.size(); ++i) {
+      std::memcpy(&hr[i * (size_t)T], &dense[(size_t)order[i] * (size_t)T], (size_t)T * 8);
+      std::memcpy(&hv[i * Tw], &valid[(size_t)order[i] * Tw], (size_t)Tw * 4);
+    }
+    std::vector<double> hq((size_t)H * (size_t)T);
+    std::vector<uint32_t> hqv((size_t)H * Tw);
+    if (H > 0 && B > 0 && T > 0) {
+      const int rc = b2p_histogram_quantile(ctx_, args_.quantile, le_bounds.data(), B, hr.data(), hv.data(), H,
+                                            (uint64_t)T, hq.data(), hqv.data());
+      if (rc != B2P_OK) throw PlanError(ErrorKind::Execution, b2p_last_error());
+    }
+    OwnedColumn* c_ts = add_col(args_.time_index, "tsm:");
+    OwnedColumn* c_val = add_col(value_name, "g");
+    std::vector<OwnedColumn*> c_tags;
+    for (size_t t = 0; t < args_.tag_columns.size(); ++t)
+      if (t != le_idx) {
+        c_tags.push_back(add_col(args_.tag_columns[t], "u"));
+        c_tags.back()->offsets.push_back(0);
+      }
+    uint32_t h = 0;
+    for (auto& kv : hist) {
+      for (int64_t k = 0; k < T; ++k) {
+        if (!((hqv[(size_t)h * Tw + (size_t)(k >> 5)] >> (k & 31)) & 1u)) continue;
+        c_ts->i64.push_back(eval_ts[(size_t)k]);
+        c_val->f64.push_back(hq[(size_t)h * (size_t)T + (size_t)k]);
+        for (size_t t = 0; t < c_tags.size(); ++t) {
+          c_tags[t]->chars += kv.first[t];
+          c_tags[t]->offsets.push_back((int32_t)c_tags[t]->chars.size());
+        }
+        ++n_out;
+      }
+      ++h;
+    }
+  } else if (agg_id_ < 0) {
     // rows of Filter(prom_fn IS NOT NULL): {time_index (eval ts), prom_fn(...), tags...}, series-major order
     OwnedColumn* c_ts = add_col(args_.time_index, "tsm:");
-    OwnedColumn* c_val = add_col(args_.function + "(" + args_.time_index + "_range," + args_.field_column + ")", "g");
+    OwnedColumn* c_val = add_col(value_name, "g");
     std::vector<OwnedColumn*> c_tags;
     for (size_t t = 0; t < args_.tag_columns.size(); ++t) {
       c_tags.push_back(add_col(args_.tag_columns[t], key_is_id_ ? "L" : "u"));
@@ -313,7 +411,7 @@ void PromRangePlan::execute(ArrowArray* out, ArrowSchema* out_schema) {
       c_by.back()->offsets.push_back(0);
     }
     OwnedColumn* c_ts = add_col(args_.time_index, "tsm:");
-    OwnedColumn* c_val = add_col(args_.aggregate + "(" + args_.function + ")", "g");
+    OwnedColumn* c_val = add_col(args_.aggregate + "(" + (fn_id_ >= 0 ? args_.function : args_.field_column) + ")", "g");
     for (const auto& kv : groups) {  // std::map iterates in key order
       const uint32_t g = kv.second;
       for (int64_t k = 0; k < T; ++k) {
@@ -434,6 +532,21 @@ b2p_plan* b2p_plan_range_create(b2p_ctx* ctx, const char* function, const b2p_ra
     g_err = e.what();
   }
   return nullptr;
+}
+
+int b2p_plan_set_instant(b2p_plan* plan, int64_t lookback_delta) {
+  if (!plan) return B2P_E_INVALID;
+  return plan->plan->set_instant(lookback_delta);
+}
+
+int b2p_plan_set_histogram_quantile(b2p_plan* plan, const char* le_column, double quantile) {
+  if (!plan || !le_column) return B2P_E_INVALID;
+  try {
+    plan->plan->set_histogram(le_column, quantile);
+    return B2P_OK;
+  } catch (const b2p::PlanError& e) {
+    return plan_fail(e);
+  }
 }
 
 int b2p_plan_push_batch(b2p_plan* plan, struct ArrowArray* batch, struct ArrowSchema* schema) {

@@ -67,6 +67,14 @@ struct PromRangePlanArgs {
   // optional prom_aggr_expr_to_plan stage: "", "sum", "avg", "count", "min", "max", "stddev", "stdvar"
   std::string aggregate;
   std::vector<std::string> by_columns;  // must be a subset of tag_columns
+  // function == "" selects the instant-vector form instead: InstantManipulate::new(start, end, lookback_delta,
+  // interval, time_index, field_column) (instant_manipulate.rs:189-208); `range` is ignored
+  Millisecond lookback_delta = 300000;
+  // optional HistogramFold::new(le_column, field, time_index, quantile) on top (histogram_fold.rs:104-130):
+  // le_column must be one of tag_columns; every histogram must expose the same bucket bounds
+  bool histogram = false;
+  std::string le_column;
+  double quantile = 0.0;
 };
 
 class PromRangePlan {
@@ -78,6 +86,14 @@ class PromRangePlan {
   // runs the sub-plan on the device and exports the result batch (caller releases it)
   void execute(ArrowArray* out, ArrowSchema* out_schema);
   int64_t num_series() const { return num_series_; }  // the reference's `num_series` metric (range_manipulate.rs:610-619)
+  // switch the node to the instant-vector form (InstantManipulate) / add a HistogramFold on top; before execute()
+  int set_instant(Millisecond lookback_delta) {
+    args_.function.clear();
+    fn_id_ = -1;
+    args_.lookback_delta = lookback_delta;
+    return 0;
+  }
+  void set_histogram(const std::string& le_column, double quantile);
 
  private:
   struct TagStore {

@@ -37,7 +37,8 @@ class PromRangeExec:
     def __init__(self, ctx: Context, function: str, start: int, end: int, interval: int, range: int, time_index: str,
                  field_column: str, tag_columns: Sequence[str], offset: int = 0, need_filter_out_nan: bool = True,
                  param0: float = 0.0, param1: float = 0.0, aggregate: Optional[str] = None,
-                 by_columns: Sequence[str] = ()):
+                 by_columns: Sequence[str] = (), lookback_delta: Optional[int] = None,
+                 histogram_quantile: Optional[float] = None, le_column: str = "le"):
         self._L = _lib.load()
         self._ctx = ctx
         p = make_params(0, start, end, interval, range, offset=offset, filter_nan=need_filter_out_nan, param0=param0,
@@ -48,6 +49,12 @@ class PromRangeExec:
                                                 (aggregate or "").encode(), by, len(by_columns))
         if not self._h:
             raise B2PError(-1, self._L.b2p_plan_last_error().decode())
+        if lookback_delta is not None:      # instant-vector selector (InstantManipulate) instead of a range function
+            self._L.b2p_plan_set_instant(self._h, int(lookback_delta))
+        if histogram_quantile is not None:  # HistogramFold on top
+            rc = self._L.b2p_plan_set_histogram_quantile(self._h, le_column.encode(), float(histogram_quantile))
+            if rc != 0:
+                raise B2PError(rc, self._L.b2p_plan_last_error().decode())
 
     def push(self, batch) -> None:
         """Feed one pyarrow.RecordBatch (moved into the plan through the C Data Interface)."""

@@ -242,6 +242,12 @@ B2P_API b2p_plan* b2p_plan_range_create(b2p_ctx* ctx, const char* function, cons
                                         const char* time_index, const char* field_column,
                                         const char* const* tag_columns, int32_t n_tags, const char* aggregate,
                                         const char* const* by_columns, int32_t n_by);
+/* Turn the node into the instant-vector form: InstantManipulate(start, end, lookback_delta, interval, ...)
+ * (instant_manipulate.rs:189-208) instead of RangeManipulate + prom_fn; `function` / range are then ignored. */
+B2P_API int b2p_plan_set_instant(b2p_plan* plan, int64_t lookback_delta);
+/* Add HistogramFold(le_column, field, time_index, quantile) (histogram_fold.rs:104-130) on top of the per-series
+ * result: series that agree on every tag except `le` form one histogram. */
+B2P_API int b2p_plan_set_histogram_quantile(b2p_plan* plan, const char* le_column, double quantile);
 B2P_API int b2p_plan_push_batch(b2p_plan* plan, struct ArrowArray* batch, struct ArrowSchema* schema);
 B2P_API int b2p_plan_execute(b2p_plan* plan, struct ArrowArray* out, struct ArrowSchema* out_schema);
 B2P_API int64_t b2p_plan_num_series(b2p_plan* plan);

@@ -113,3 +113,42 @@ def test_tsid_key_and_errors(ctx):
     with pytest.raises(B2PError) as ei:
         ex2.push(b)
     assert "No field named timestamp" in str(ei.value)
+
+
+def test_histogram_quantile_through_the_plan(ctx):
+    """tql eval (2820,2820,'1s') histogram_quantile(phi, rate(histogram2_bucket[15m])) — simple_histogram.result:237-262:
+    SeriesDivide by the `le` tag, rate per bucket series, HistogramFold on top."""
+    from greptimedb_b200.plan import PromRangeExec
+    case = next(c for c in SQL["histogram_cases"] if c["name"] == "histogram2_rate_15m")
+    les = ["0", "2", "4", "6", "+Inf"]
+    # the scan delivers rows sorted by the primary key (le as a STRING: "+Inf" < "0" < "2" ...) then ts
+    order = sorted(range(len(les)), key=lambda i: les[i])
+    ts, val, le = [], [], []
+    for i in order:
+        ts += case["bucket_ts"]
+        val += case["bucket_val"][i]
+        le += [les[i]] * len(case["bucket_ts"])
+    b = pa.record_batch([pa.array(ts, pa.timestamp("ms")), pa.array(val, pa.float64()), pa.array(le)],
+                        names=["ts", "val", "le"])
+    for q, expected in case["quantiles"]:
+        ex = PromRangeExec(ctx, "prom_rate", case["start"], case["end"], case["interval"], case["range"], "ts", "val",
+                           ["le"], histogram_quantile=q)
+        ex.push(b)
+        out = ex.execute()
+        assert out.schema.names == ["ts", "prom_rate(ts_range,val)"]
+        assert out.column(1).to_pylist() == [expected], (q, out.column(1).to_pylist())
+
+
+def test_instant_selector_through_the_plan(ctx):
+    """tql eval (3000,3000,'1s') calculate_rate_offset_total offset 10m — promql/offset.result:85-92."""
+    from greptimedb_b200.plan import PromRangeExec
+    case = next(c for c in SQL["instant_cases"] if c["name"] == "instant_offset_10m_at_3000")
+    ex = PromRangeExec(ctx, "", case["start"], case["end"], case["interval"], 0, "ts", "val", ["x"],
+                       offset=case["offset"], lookback_delta=case["lookback"])
+    for bb in batch_from_series(case["series"], split=5):
+        ex.push(bb)
+    out = ex.execute()
+    assert out.schema.names == ["ts", "val", "x"]
+    rows = list(zip(out.column(2).to_pylist(), [int(t.timestamp() * 1000) for t in out.column(0).to_pylist()],
+                    out.column(1).to_pylist()))
+    assert rows == [tuple(r) for r in case["expected"]]
