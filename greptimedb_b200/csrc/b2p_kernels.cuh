@@ -347,32 +347,16 @@ __device__ __forceinline__ void process_steps(const RangeArgs& a, SeriesState& s
   }
 }
 
-// One lane's step once its window [lo, lo+l) and edge timestamps are known.
-template <int FN, int RING, bool TS32>
-__device__ __forceinline__ bool eval_lane(const RangeArgs& a, const RingAcc<RING, TS32>& acc, uint32_t lo, uint32_t l,
-                                          typename TimeDom<TS32>::type t_lo, typename TimeDom<TS32>::type t_hi,
-                                          typename TimeDom<TS32>::type te, typename TimeDom<TS32>::type rng, double& r) {
-  if constexpr (FnTraits<FN>::kExtrapolated) {
-    if (l < 2) return false;
-    r = extrapolated_value<FN>(acc, lo, l, t_lo, t_hi, te, rng, a.range_secs, a.rcp_rs);
-    return true;
-  } else {
-    const bool ok = eval_window<FN>(acc, lo, l, te, rng, a.p0, a.p1, a.rcp_rs, r);
-    if (!ok) r = 0.0;
-    return ok;
-  }
-}
-
 // Steady-state variant of process_steps: a whole aligned group of 32 steps, every step inside the
 // series' evaluated grid [kf, kl], ring non-empty.  No per-lane activity predicates; when consecutive
 // steps advance both window edges by exactly one sample (stride 1: step == scrape interval) each lane
-// reads ONE timestamp per edge and gets its neighbour's through a shuffle, and — once verified — all the
-// warp-uniform bookkeeping is known without any further exchange.
+// reads ONE timestamp per edge and gets its neighbour's through a shuffle.
 template <int FN, int RING, bool TS32>
 __device__ __forceinline__ void process_group_full(const RangeArgs& a, SeriesState& st, RingAcc<RING, TS32>& acc,
                                                    double* out_grp, uint32_t* vw_grp, int32_t k_a, int lane) {
   using TD = TimeDom<TS32>;
   using time_type = typename TD::type;
+  using TR = FnTraits<FN>;
   const int32_t k = k_a + lane;
   const time_type tlo = TD::tlo(a, k);
   const time_type rng = TD::range(a);
@@ -383,7 +367,6 @@ __device__ __forceinline__ void process_group_full(const RangeArgs& a, SeriesSta
   time_type t_hi = 0, t_lo = 0;  // ts[g], ts[q] when the guess verified
   bool good;
   acc.set_window((int32_t)st.base_lo - 16);
-  acc.no_flags = st.last_flag <= st.base_lo;
   const bool unit_stride = st.stride_hi == 1 && st.stride_lo == 1 && st.base_hi >= 0 && st.base_hi + 33 <= top &&
                            (int32_t)st.base_lo + 32 <= top;
   if (unit_stride) {
@@ -396,23 +379,6 @@ __device__ __forceinline__ void process_group_full(const RangeArgs& a, SeriesSta
     t_lo = __shfl_down_sync(0xffffffffu, t_lo_prev, 1);
     if (lane == 31) t_lo = acc.t(q);
     good = (t_hi <= te) && (t_hi_next > te) && (t_lo_prev <= tlo) && (t_lo > tlo) && ((int32_t)q <= g);
-    if (__all_sync(0xffffffffu, good)) {
-      // ---- the common case, straight through ----------------------------------------------------------
-      double r = 0.0;
-      const bool ok = eval_lane<FN, RING, TS32>(a, acc, q, (uint32_t)(g + 1 - (int32_t)q), t_lo, t_hi, te, rng, r);
-      // every window is non-empty, followed by a sample and starts one ordinal after its predecessor's:
-      // c0 = (lo-1) + 1 = lo < j_cnt for every lane, so only the carried c0 of the previous group can matter
-      if (st.carry_c0 >= st.j_cnt) st.max_c0 = max(st.max_c0, st.carry_c0);
-      st.base_hi += 32;
-      st.base_lo += 32;  // both strides stay 1
-      st.carry_c0 = st.base_lo;
-      st.lrs = st.base_lo;
-      st.any_nonempty = true;
-      *out_grp = r;
-      const uint32_t vw = __ballot_sync(0xffffffffu, ok);
-      if (lane == 0) *vw_grp = vw;
-      return;
-    }
   } else {
     g = st.base_hi + (lane + 1) * st.stride_hi;
     g = g > top ? top : g;
@@ -428,7 +394,8 @@ __device__ __forceinline__ void process_group_full(const RangeArgs& a, SeriesSta
     t_hi = tg;
     t_lo = tq;
   }
-  if (!__all_sync(0xffffffffu, good)) {  // some guess missed: every lane walks (zero steps where it was right)
+  const bool all_good = __all_sync(0xffffffffu, good);
+  if (!all_good) {  // some guess missed: every lane walks (zero steps where it was right)
     while (g < top && acc.t((uint32_t)(g + 1)) <= te) ++g;
     while (g > st.base_hi && acc.t((uint32_t)g) > te) --g;
     const uint32_t qtop = (uint32_t)(g + 1);
@@ -441,15 +408,42 @@ __device__ __forceinline__ void process_group_full(const RangeArgs& a, SeriesSta
   const int32_t hi = g;
   const uint32_t lo = q;
   const uint32_t l = ((int32_t)lo <= hi) ? (uint32_t)(hi + 1 - (int32_t)lo) : 0u;
+  acc.no_flags = st.last_flag <= st.base_lo;
   double r = 0.0;
-  const bool ok = eval_lane<FN, RING, TS32>(a, acc, lo, l, t_lo, t_hi, te, rng, r);
+  bool ok;
+  if constexpr (TR::kExtrapolated) {
+    ok = l >= 2;
+    if (ok) r = extrapolated_value<FN>(acc, lo, l, t_lo, t_hi, te, rng, a.range_secs, a.rcp_rs);
+  } else {
+    ok = eval_window<FN>(acc, lo, l, te, rng, a.p0, a.p1, a.rcp_rs, r);
+    if (!ok) r = 0.0;
+  }
 
   // cursor-overshoot watch (see process_steps)
   const int32_t nhi = __shfl_sync(0xffffffffu, hi, 31);
   const uint32_t nlo = __shfl_sync(0xffffffffu, lo, 31);
   const bool nonempty = l > 0;
-  const uint32_t ne_mask = __ballot_sync(0xffffffffu, nonempty);
-  if (ne_mask) {
+  uint32_t ne_mask = 0xffffffffu;
+  if (unit_stride && all_good) {
+    // every window is non-empty, followed by a sample, and starts one ordinal after its predecessor's:
+    // c0 = (lo-1) + 1 = lo < j_cnt for every lane, so only the carried c0 of the previous group can matter
+    if (st.carry_c0 >= st.j_cnt) st.max_c0 = max(st.max_c0, st.carry_c0);
+    st.carry_c0 = nlo;
+    st.lrs = nlo;
+    st.any_nonempty = true;
+  } else if ((ne_mask = __ballot_sync(0xffffffffu, nonempty)) == 0xffffffffu) {
+    const bool brk = (hi + 1 < (int32_t)st.j_cnt);
+    const uint32_t rsi = (brk && lo > 0) ? lo - 1 : lo;
+    uint32_t prev_lo = __shfl_up_sync(0xffffffffu, lo, 1);
+    if (lane == 0) prev_lo = st.lrs;
+    const uint32_t c0 = rsi + (lo - prev_lo);
+    uint32_t watch = (lane < 31) ? c0 : 0u;
+    if (lane == 0) watch = max(watch, st.carry_c0);
+    if (__any_sync(0xffffffffu, watch >= st.j_cnt)) st.max_c0 = max(st.max_c0, __reduce_max_sync(0xffffffffu, watch));
+    st.carry_c0 = __shfl_sync(0xffffffffu, c0, 31);
+    st.lrs = nlo;
+    st.any_nonempty = true;
+  } else if (ne_mask) {
     const bool brk = (hi + 1 < (int32_t)st.j_cnt);
     const uint32_t rsi = (brk && lo > 0) ? lo - 1 : lo;
     const uint32_t before = ne_mask & ((1u << lane) - 1u);
@@ -624,24 +618,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_
           k_fin = kk < 0 ? 0 : (kk > (int64_t)T ? T : (int32_t)kk);
         }
         k_fin = k_fin > T ? T : k_fin;
-        // steady state: whole aligned groups only (a partial group waits for the next block); here every
-        // step is <= T-1, the ring is non-empty, and k_next is aligned unless a pressure flush left it mid-group
-        {
-          const int32_t upto = k_fin & ~31;
-          while (st.k_next < upto) {
-            if (st.j_cnt - st.base_lo > (uint32_t)(RING - 32)) { defer = true; break; }
-            if ((st.k_next & 31) == 0 && st.k_next >= st.kf) {
-              process_group_full<FN, RING, TS32>(a, st, acc, out_grp, vw_grp, st.k_next, lane);
-              st.k_next += 32;
-            } else {
-              const int32_t g_end = (st.k_next | 31) + 1;  // <= upto because upto is aligned
-              process_steps<FN, RING, TS32>(a, st, acc, out_grp, vw_grp, st.k_next, g_end, T - 1, lane);
-              st.k_next = g_end;
-            }
-            out_grp += 32;
-            vw_grp += 1;
-          }
-        }
+        // steady state: whole aligned groups only (a partial group waits for the next block)
+        B2P_RUN_STEPS(k_fin & ~31, T - 1);
       }
       // ---- ring pressure: evaluate what is final, drop samples no future window can reach -----------
       if (!defer && more && st.j_cnt + 64u - st.base_lo > (uint32_t)(RING - 32)) {
