@@ -563,3 +563,61 @@ def test_column_reduce_config5_shape(ctx):
     assert np.allclose(s, 2 * np.nansum(data, 1), rtol=1e-11, atol=0)
     avg = s / c
     assert np.allclose(avg, np.nanmean(data, 1), rtol=1e-11)
+
+
+def _fuzz_series(rng, n_series):
+    """Random series zoo: regular / jittered / gappy / bursty / duplicate timestamps / NaN runs / tiny / empty."""
+    ts_l, val_l, offs = [], [], [0]
+    t_base = int(rng.integers(-5_000_000, 5_000_000))
+    for _ in range(n_series):
+        kind = int(rng.integers(0, 8))
+        n = int(rng.integers(0, 260)) if kind else int(rng.integers(0, 3))
+        scrape = int(rng.choice([1_000, 5_000, 15_000, 60_000]))
+        if kind in (1, 2):
+            t = t_base + np.arange(n) * scrape + (rng.integers(0, max(scrape // 3, 1), n) if kind == 2 else 0)
+        elif kind == 3:
+            t = t_base + np.cumsum(rng.choice([scrape, scrape, 20 * scrape], n))
+        elif kind == 4:
+            t = t_base + np.cumsum(rng.integers(1, 200, n))                  # dense burst: many samples per step
+        elif kind == 5:
+            t = t_base + np.cumsum(rng.integers(0, 2, n) * scrape)           # duplicate timestamps
+        else:
+            t = t_base + np.sort(rng.integers(0, 3_000_000, n))
+        v = np.cumsum(rng.random(n) * rng.choice([0.0, 1.0, 100.0]))
+        if n and rng.random() < 0.5:
+            for i in np.flatnonzero(rng.random(n) < 0.06):
+                v[i:] -= v[i] * rng.random()
+        if n and rng.random() < 0.4:
+            v[rng.random(n) < 0.1] = np.nan
+        if n and rng.random() < 0.1:
+            v[:] = np.nan
+        ts_l.append(np.asarray(t, np.int64))
+        val_l.append(np.asarray(v, np.float64))
+        offs.append(offs[-1] + n)
+    return np.concatenate(ts_l), np.concatenate(val_l), np.array(offs, np.uint64), t_base
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_random_queries_match_oracle(ctx, ctx_thread_tier, seed):
+    """Random series zoo x random (start, end, interval, range, offset): validity bit-exact, values <= 1e-9 rel."""
+    from greptimedb_b200 import make_params
+    rng = np.random.default_rng(1000 + seed)
+    ts, val, offsets, t_base = _fuzz_series(rng, 40)
+    fns = ["rate", "increase", "delta", "irate", "resets", "changes", "count_over_time", "avg_over_time", "max_over_time",
+           "last_over_time", "stddev_over_time", "deriv", "quantile_over_time", "absent_over_time"]
+    for _ in range(5):
+        interval = int(rng.choice([1_000, 7_000, 15_000, 60_000, 300_000]))
+        rng_ms = int(rng.choice([1, 999, 5_000, 60_000, 300_000, 900_000]))
+        start = t_base + int(rng.integers(-400_000, 1_000_000))
+        end = start + int(rng.integers(0, 400)) * interval + int(rng.integers(0, interval))
+        offset = int(rng.choice([0, 0, 30_000, -45_000]))
+        for fn in rng.choice(fns, 4, replace=False):
+            fn = str(fn)
+            p = make_params(fn, start, end, interval, rng_ms, offset=offset, param0=0.75)
+            op = orc.make_params(fn, start, end, interval, rng_ms, offset=offset, param0=0.75)
+            e_out, e_valid = orc.range_query(op, ts, val, None, offsets)
+            for c in ((ctx, ctx_thread_tier) if fn in ("rate", "increase", "delta") else (ctx,)):
+                out, valid, ets = c.range_eval(p, ts, val, offsets=offsets)
+                assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size),
+                             f"fuzz seed={seed} {fn} start={start} end={end} int={interval} rng={rng_ms} off={offset}",
+                             bit_exact=fn in BIT_EXACT)
