@@ -316,6 +316,9 @@ def run_ours(args):
     k0 = statistics.mean(k0_ms) if k0_ms else float("nan")
     alg_k2 = 16.0 * n_rows + 8.0 * S * T + 4.0 * S * Tw + 8.0 * (S + 1)   # bytes per launch of the dominant kernel
     achieved = alg_k2 / (k2 * 1e-3) / 1e9
+    lean_on = os.environ.get("B2P_DISABLE_LEAN_TIER", "0") != "1" and os.environ.get("B2P_ENABLE_THREAD_TIER", "0") != "1"
+    kernel_name = ("range_lean_kernel<rate> (+ range_fast_kernel<rate> over the series it hands off)" if lean_on
+                   else "range_fast_kernel<rate>")
     step_ms = elapsed_ms / args.steps
     read_frac = 20.0 * n_rows / (step_ms * 1e-3) / 1e9 / peak
     line = {
@@ -329,7 +332,7 @@ def run_ours(args):
                    "parallelism": f"series-sharded x{world}, " + ("one all-reduce of [G x T] (sum f64, cnt i32) per step"
                                                                   if sumby else "no data-path collective"),
                    "l2": "inputs (16-25 GB per step) >> 126 MB L2; no flush needed"},
-        "roofline": {"bound": "hbm", "kernel": "range_fast_kernel<rate>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
                      # capture (profiles/r1_range_fast_kernel.md, version f, 2e8-sample launch: 3.381 + 1.585 GB), scaled

@@ -16,6 +16,7 @@
 #include "../../include/b200promql.h"
 #include "b2p_aggregate.cuh"
 #include "b2p_kernel_t.cuh"
+#include "b2p_kernel_lean.cuh"
 #include "b2p_kernels.cuh"
 
 using namespace b2p;
@@ -87,6 +88,9 @@ struct b2p_ctx {
   // K2T (thread per series) in front of K2 for rate/increase/delta.  Measured slower than K2 on B200
   // (28 vs 64 G samples/s, profiles/r1_thread_tier.md), so it is opt-in: B2P_ENABLE_THREAD_TIER=1.
   bool thread_tier = false;
+  // K2L, the lean warp-per-series tier in front of K2 (default on; B2P_DISABLE_LEAN_TIER=1 turns it off)
+  bool lean_tier = true;
+  int lean_blocks_per_sm[3] = {0, 0, 0};
   size_t arena_rows = 0;
   cudaEvent_t ev[4][2] = {};
   bool ev_used[4] = {false, false, false, false};
@@ -161,9 +165,42 @@ bool fits_ts32(const RangeArgs& a) {
   return span >= 0 && span < 2147483000.0 && a.interval < 2147483000ll && a.range < 2147483000ll;
 }
 
+bool lean_ok(const b2p_ctx* c, int fn, const RangeArgs& a) {
+  if (!c->lean_tier || !(fn == B2P_FN_RATE || fn == B2P_FN_INCREASE || fn == B2P_FN_DELTA)) return false;
+  if (!fits_ts32(a) || a.rcp_rs == 0.0 || a.range < a.interval || a.start < 0) return false;
+  return (double)a.rel_max + 64.0 * (double)a.interval < 4294967295.0;
+}
+
 template <int FN>
 int launch_fast(b2p_ctx* c, const RangeArgs& a) {
   return fits_ts32(a) ? launch_fast_t<FN, true>(c, a) : launch_fast_t<FN, false>(c, a);
+}
+
+// Lean first tier (K2L): rate / increase / delta in the 32-bit time domain.  The gates are what the kernel
+// relies on: exact reciprocal division by range/1000, range >= interval (steps evaluated before the end of a
+// series are below the trimmed end), start >= 0 (truncating division == floor in the end trim), and window
+// ends of the 31 steps past the grid still below the 0xFFFFFFFF end sentinel.
+bool lean_ok(const b2p_ctx* c, int fn, const RangeArgs& a);
+
+template <int FN>
+int launch_lean(b2p_ctx* c, const RangeArgs& a) {
+  constexpr size_t smem = (size_t)kWarpsPerCta * 2 * kLeanRing * 12 + kRcpTable * 8;
+  auto kern = range_lean_kernel<FN>;
+  int& cached = c->lean_blocks_per_sm[FN];
+  if (cached == 0) {
+    int nb = 0;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarpsPerCta * 32, smem));
+    cached = nb > 0 ? nb : 1;
+  }
+  const unsigned need = (a.n_series + kWarpsPerCta - 1) / kWarpsPerCta;
+  const unsigned cap = (unsigned)(c->num_sms * cached);
+  const unsigned grid = need < cap ? need : cap;
+  if (grid == 0) return B2P_OK;
+  kern<<<grid, kWarpsPerCta * 32, smem, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return B2P_OK;
 }
 
 template <int FN>
@@ -317,6 +354,7 @@ b2p_ctx* b2p_create(int device) {
     }
   }
   if (const char* e = getenv("B2P_ENABLE_THREAD_TIER")) c->thread_tier = (e[0] == '1');
+  if (const char* e = getenv("B2P_DISABLE_LEAN_TIER")) c->lean_tier = !(e[0] == '1');
   return c;
 }
 
@@ -466,6 +504,7 @@ int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts,
     a.rcp_rs = (p->range > 0 && !all_ones) ? 1.0 / rs : 0.0;
     a.range_secs = rs;
     a.rcp_interval = 1.0 / (double)p->interval;
+    a.start_mod = p->start >= 0 ? (uint32_t)(p->start % p->interval) : 0u;
   }
   a.ts = ts; a.val = val; a.offsets = offsets; a.n_rows = n_rows; a.n_series = n_series;
   a.out = out; a.valid = valid_words;
@@ -487,6 +526,12 @@ int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts,
     if (p->fn_id == B2P_FN_RATE) rc = launch_thread_tier<B2P_FN_RATE>(c, a);
     else if (p->fn_id == B2P_FN_INCREASE) rc = launch_thread_tier<B2P_FN_INCREASE>(c, a);
     else rc = launch_thread_tier<B2P_FN_DELTA>(c, a);
+    if (rc) return rc;
+    a.use_w_list = 1;
+  } else if (lean_ok(c, p->fn_id, a)) {
+    if (p->fn_id == B2P_FN_RATE) rc = launch_lean<B2P_FN_RATE>(c, a);
+    else if (p->fn_id == B2P_FN_INCREASE) rc = launch_lean<B2P_FN_INCREASE>(c, a);
+    else rc = launch_lean<B2P_FN_DELTA>(c, a);
     if (rc) return rc;
     a.use_w_list = 1;
   }
@@ -858,7 +903,7 @@ int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, con
   CU(cudaStreamSynchronize(c->s_d2h));
   c->pending_range = false;
   // per-chunk verdicts; a chunk whose slow path ran out of arena is redone alone (b2p_sync grows the arena)
-  long long slow_total = 0;
+  long long slow_total = 0, w_total = 0;
   row_lo = 0;
   for (uint32_t i = 0; i < n_chunks; ++i) {
     const uint32_t s0 = i * C;
@@ -866,6 +911,7 @@ int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, con
     const uint64_t row_hi = offsets_host ? offsets_host[s1] : lower_bound_sid(sid, n_rows, s1);
     const Status st = h_stat[i];
     slow_total += st.slow_count;
+    w_total += st.w_count;
     if (st.k0_errors & 1u) return fail(B2P_E_UNSORTED, "series-id column is not non-decreasing");
     if (st.k0_errors & 2u) return fail(B2P_E_UNSORTED, "series id >= n_series");
     if (st.arena_overflow) {
@@ -885,6 +931,7 @@ int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, con
     row_lo = row_hi;
   }
   c->last_slow = slow_total;
+  c->last_w = w_total;
   return B2P_OK;
 }
 

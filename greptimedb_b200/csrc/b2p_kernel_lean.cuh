@@ -1,0 +1,358 @@
+// b2p_kernel_lean.cuh — K2L: the lean first tier of the fused range kernel (rate / increase / delta).
+//
+// Same contract as range_fast_kernel (SeriesNormalize -> RangeManipulate -> prom_rate/increase/delta ->
+// IS NOT NULL for every series of the batch, one warp per series, samples streamed into a per-warp
+// shared-memory ring, one eval step per lane), but it only keeps the work the common series needs and hands
+// every series that needs more to range_fast_kernel through RangeArgs::w_list (which in turn hands the
+// cursor-overshoot / long-window cases to range_slow_kernel).  A series stays on this tier while
+//   * no sample is dropped by SeriesNormalize (normalize.rs:417-426: NaN values with filter_nan),
+//   * no counter reset occurs (extrapolate_rate.rs:226-233 would add a correction),
+//   * every window and the 64-row block behind it fit the ring,
+//   * the windows of the evaluated steps are empty only before the first and after the last non-empty one,
+//   * calculate_range's cursor start (range_manipulate.rs:741) stays below the number of
+//     samples of the series wherever the next window is non-empty (the overshoot quirk needs the slow kernel).
+// What it does evaluate is bit-identical to the second tier: window edges are the definitional ones
+// (verified guesses, else a walk), the arithmetic is the same extrapolate_parts.
+//
+// Differences that make it cheap:
+//   * sentinels instead of bounds: ring slot -1 holds (ts 0, -inf) and, after the last row, slot m holds
+//     ts 0xFFFFFFFF, so neither the verification reads nor the walks need index guards;
+//   * readiness without division: a group of 32 steps is evaluated as soon as the window end of its last
+//     step is older than the newest sample (te31 < t_new), tracked incrementally;
+//   * proportional edge guesses (lane+1)*d/32 from the previous group's total advance, verified by four
+//     ring reads; when they hold, the next bases follow without shuffles;
+//   * the end trim (range_manipulate.rs:722-728) is applied to the tail groups only — every step
+//     evaluated before the end of the stream is below the trimmed end when range >= interval (host gate).
+#pragma once
+#include "b2p_kernels.cuh"
+
+namespace b2p {
+
+#ifndef B2P_LEAN_MIN_BLOCKS
+#define B2P_LEAN_MIN_BLOCKS 3
+#endif
+constexpr int kLeanRing = 256;
+
+struct LeanState {  // warp-uniform
+  uint32_t j_cnt;    // samples in the ring's ordinal space (== rows consumed: nothing is filtered on this tier)
+  uint32_t base_lo;  // window start of the last evaluated step (in phase 1 also calculate_range's last_range_start)
+  int32_t base_hi;   // window end (index) of the last evaluated step
+  uint32_t d_lo, d_hi;  // advance of both edges over the previous group (32 steps)
+  // 0 = no non-empty window yet (last_range_start is still 0), 1 = inside the run of non-empty windows,
+  // 2 = after it, 3 = like 1 but the cursor start handed to the next step is >= m: a non-empty window there
+  // would hit the overshoot quirk
+  uint32_t phase;
+};
+
+// One aligned group of 32 steps; lane's step is k (window end te, start tlo = te - range, both in the 32-bit
+// domain).  Returns 0, or the reason (> 0) why the series has to go to the second tier.
+template <int FN, bool TAIL>
+__device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, RingAcc<kLeanRing, true>& acc,
+                                           uint32_t m, uint32_t te, int32_t k, int32_t kl, double* out_p,
+                                           uint32_t* vw_p, int lane) {
+  const uint32_t rng = (uint32_t)a.range;
+  const uint32_t tlo = te - rng;
+  const int32_t top = (int32_t)st.j_cnt - 1;
+  const uint32_t lane1 = (uint32_t)lane + 1u;
+  acc.set_window((int32_t)st.base_lo - 1);
+  int32_t g = st.base_hi + (int32_t)((lane1 * st.d_hi) >> 5);
+  uint32_t q = st.base_lo + ((lane1 * st.d_lo) >> 5);
+  // before the end of the stream the newest sample is younger than every window end of the group, so a
+  // window ends below it; afterwards slot top+1 holds the end sentinel.  Either way g+1 and q stay on
+  // written slots.
+  const int32_t gmax = TAIL ? top : top - 1;
+  g = g > gmax ? gmax : g;
+  q = q > (uint32_t)(g + 1) ? (uint32_t)(g + 1) : q;
+  uint32_t t_hi = acc.t((uint32_t)g);
+  const uint32_t t_hi1 = acc.t((uint32_t)(g + 1));
+  const uint32_t t_lo1 = acc.t(q - 1u);
+  uint32_t t_lo = acc.t(q);
+  const bool good = (t_hi <= te) && (t_hi1 > te) && (t_lo1 <= tlo) && (t_lo > tlo) && ((int32_t)q <= g);
+  // uniform: the previous step had a non-empty window and no cursor start of this group can reach the end of
+  // the series.  A cursor start is lo - 1 + (advance of lo) while a younger sample follows the window: before
+  // the end of the stream, with at most one sample of advance per step (d_lo <= 32), that is at most
+  // lo <= hi <= top - 1, so verified guesses imply it; otherwise bound it by base_lo + d_lo + ceil(d_lo/32).
+  bool uni = st.phase == 1u;
+  if (TAIL || st.d_lo > 32u) uni = uni && (st.base_lo + st.d_lo + ((st.d_lo + 31u) >> 5) < m);
+  if (uni && __all_sync(0xffffffffu, good)) {
+    st.base_hi += (int32_t)st.d_hi;
+    st.base_lo += st.d_lo;
+  } else {
+    // some guess missed (or the state is not the steady one): every lane walks to the definitional edges;
+    // the sentinels bound all four walks
+    while (acc.t((uint32_t)(g + 1)) <= te) ++g;
+    while (acc.t((uint32_t)g) > te) --g;
+    q = q > (uint32_t)(g + 1) ? (uint32_t)(g + 1) : q;
+    while (acc.t(q - 1u) > tlo) --q;
+    while (acc.t(q) <= tlo) ++q;
+    t_hi = acc.t((uint32_t)g);
+    t_lo = acc.t(q);
+    const bool ne = (int32_t)q <= g;
+    const uint32_t ne_mask = __ballot_sync(0xffffffffu, ne);
+    // empty windows are only tolerated before the first and after the last non-empty one
+    if (ne_mask) {
+      const int first = __ffs(ne_mask) - 1, last = 31 - __clz(ne_mask);
+      const bool contiguous = (ne_mask >> first) == (0xffffffffu >> (31 - (last - first)));
+      if (!contiguous || st.phase == 2u || (st.phase == 1u && first != 0)) return 1;
+      if (st.phase == 3u) return 2;
+      // exact cursor start after each non-empty step (range_manipulate.rs:741,757,765-768)
+      const bool brk = g < top;
+      const uint32_t rsi = (brk && q > 0u) ? q - 1u : q;
+      uint32_t prev = __shfl_up_sync(0xffffffffu, q, 1);
+      if (lane == first) prev = (st.phase == 1u) ? st.base_lo : 0u;  // last_range_start
+      const uint32_t c0 = ne ? rsi + (q - prev) : 0u;
+      const bool next_ne = (lane < 31) && ((ne_mask >> (lane + 1)) & 1u);
+      if (__any_sync(0xffffffffu, next_ne && c0 >= m)) return 2;
+      const uint32_t carry = __shfl_sync(0xffffffffu, c0, 31);  // 0 when lane 31's window is empty
+      st.phase = (last == 31) ? (carry >= m ? 3u : 1u) : 2u;
+    } else if (st.phase == 1u || st.phase == 3u) {
+      st.phase = 2u;
+    }
+    const int32_t nhi = __shfl_sync(0xffffffffu, g, 31);
+    const uint32_t nlo = __shfl_sync(0xffffffffu, q, 31);
+    st.d_hi = (uint32_t)(nhi - st.base_hi);
+    st.d_lo = nlo - st.base_lo;
+    st.base_hi = nhi;
+    st.base_lo = nlo;
+  }
+  const uint32_t l = (uint32_t)(g + 1) - q;  // 0 for an empty window (q == g + 1)
+  bool ok = (int32_t)l >= 2;
+  if (TAIL) ok = ok && (k <= kl);
+  double r = 0.0;
+  if (ok) {
+    const double first_value = acc.v(q);
+    const double last_value = acc.v((uint32_t)g);
+    // counters add the reset correction, 0.0 on this tier (keeps the sign of a zero difference identical)
+    const double result_value = FnTraits<FN>::kCounter ? (last_value - first_value) + 0.0 : last_value - first_value;
+    r = extrapolate_parts<FN, uint32_t, true>(result_value, first_value, t_lo, t_hi, l, te, rng,
+                                              acc.rcp(l - 1u), a.range_secs, a.rcp_rs);
+  }
+  if (!TAIL || k < (int32_t)a.T) *out_p = r;
+  const uint32_t vw = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) *vw_p = vw;
+  return 0;
+}
+
+
+#ifndef B2P_LEAN_PAIR
+#define B2P_LEAN_PAIR 1
+#endif
+
+// The value of one step whose window [q, g] (both edge timestamps known) has already been verified.
+template <int FN>
+__device__ __forceinline__ double lean_value(const RangeArgs& a, const RingAcc<kLeanRing, true>& acc, int32_t g,
+                                             uint32_t q, uint32_t t_lo, uint32_t t_hi, uint32_t te, bool& ok) {
+  const uint32_t l = (uint32_t)(g + 1) - q;
+  ok = (int32_t)l >= 2;
+  double r = 0.0;
+  if (ok) {
+    const double first_value = acc.v(q);
+    const double last_value = acc.v((uint32_t)g);
+    const double result_value = FnTraits<FN>::kCounter ? (last_value - first_value) + 0.0 : last_value - first_value;
+    r = extrapolate_parts<FN, uint32_t, true>(result_value, first_value, t_lo, t_hi, l, te, (uint32_t)a.range,
+                                              acc.rcp(l - 1u), a.range_secs, a.rcp_rs);
+  }
+  return r;
+}
+
+// Two consecutive groups (64 steps) in one go, steady state only: before the end of the stream, previous step
+// non-empty, at most one sample of advance per step (so no cursor start can reach m, see lean_group), and every
+// one of the 64 proportional guesses verified by one vote.  Returns false without side effects when any of that
+// does not hold; the caller then takes the groups one at a time.
+template <int FN>
+__device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, RingAcc<kLeanRing, true>& acc, uint32_t te,
+                                          uint32_t step32, double* out_p, uint32_t* vw_p, int lane) {
+  const int32_t top = (int32_t)st.j_cnt - 1;
+  // uniform gates; the last two keep every read below the newest sample (slot top), i.e. on written slots
+  if (st.phase != 1u || st.d_lo > 32u || st.base_hi + 2 * (int32_t)st.d_hi >= top || st.base_lo + 2u * st.d_lo > (uint32_t)top)
+    return false;
+  const uint32_t rng = (uint32_t)a.range;
+  const uint32_t lane1 = (uint32_t)lane + 1u;
+  const uint32_t te_b = te + step32;
+  const uint32_t tlo_a = te - rng, tlo_b = te_b - rng;
+  acc.set_window((int32_t)st.base_lo - 1);
+  const int32_t g_a = st.base_hi + (int32_t)((lane1 * st.d_hi) >> 5), g_b = g_a + (int32_t)st.d_hi;
+  const uint32_t q_a = st.base_lo + ((lane1 * st.d_lo) >> 5), q_b = q_a + st.d_lo;
+  const uint32_t t_hi_a = acc.t((uint32_t)g_a), t_hi1_a = acc.t((uint32_t)(g_a + 1));
+  const uint32_t t_lo1_a = acc.t(q_a - 1u), t_lo_a = acc.t(q_a);
+  const uint32_t t_hi_b = acc.t((uint32_t)g_b), t_hi1_b = acc.t((uint32_t)(g_b + 1));
+  const uint32_t t_lo1_b = acc.t(q_b - 1u), t_lo_b = acc.t(q_b);
+  const bool good = (t_hi_a <= te) && (t_hi1_a > te) && (t_lo1_a <= tlo_a) && (t_lo_a > tlo_a) && ((int32_t)q_a <= g_a) &&
+                    (t_hi_b <= te_b) && (t_hi1_b > te_b) && (t_lo1_b <= tlo_b) && (t_lo_b > tlo_b) && ((int32_t)q_b <= g_b);
+  if (!__all_sync(0xffffffffu, good)) return false;
+  st.base_hi += 2 * (int32_t)st.d_hi;
+  st.base_lo += 2u * st.d_lo;
+  bool ok_a, ok_b;
+  const double r_a = lean_value<FN>(a, acc, g_a, q_a, t_lo_a, t_hi_a, te, ok_a);
+  out_p[0] = r_a;
+  const double r_b = lean_value<FN>(a, acc, g_b, q_b, t_lo_b, t_hi_b, te_b, ok_b);
+  out_p[32] = r_b;
+  const uint32_t vw_a = __ballot_sync(0xffffffffu, ok_a), vw_b = __ballot_sync(0xffffffffu, ok_b);
+  if (lane == 0) {
+    vw_p[0] = vw_a;
+    vw_p[1] = vw_b;
+  }
+  return true;
+}
+
+template <int FN>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_lean_kernel(const RangeArgs a) {
+  constexpr int RING = kLeanRing;
+  using TR = FnTraits<FN>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // smem: [warps][2*RING] val f64 | [warps][2*RING] ts u32 | [kRcpTable] f64
+  double* rval = reinterpret_cast<double*>(smem_raw) + warp * (2 * RING);
+  uint32_t* rts = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kWarpsPerCta * 2 * RING * 8) + warp * (2 * RING);
+  double* rcp_tab = reinterpret_cast<double*>(smem_raw + (size_t)kWarpsPerCta * 2 * RING * 12);
+  for (int i = threadIdx.x; i < kRcpTable; i += blockDim.x) rcp_tab[i] = (i > 0) ? 1.0 / (double)i : 0.0;
+  __syncthreads();
+  RingAcc<RING, true> acc{rts, rval, nullptr, rcp_tab, rts, rval, true};
+  const uint32_t total_warps = gridDim.x * kWarpsPerCta;
+  const int32_t T = (int32_t)a.T;
+  const long long tb_off = a.tb - a.offset;  // rel = ts + offset - tb
+  const uint32_t step32 = 32u * (uint32_t)a.interval;
+  const uint32_t te_lane0 = (uint32_t)a.range + (uint32_t)lane * (uint32_t)a.interval;
+  const uint32_t te31_minus_tlo0 = (uint32_t)a.range + 31u * (uint32_t)a.interval;  // te of step k+31 minus tlo of step k
+
+  for (uint32_t s = blockIdx.x * kWarpsPerCta + warp; s < a.n_series; s += total_warps) {
+    const uint64_t row0 = a.offsets[s], row1 = a.offsets[s + 1];
+    const uint32_t n = (uint32_t)(row1 - row0);
+    int defer = ((n == 0u) || (row1 - row0 > 0xfffffff0ull)) ? 3 : 0;  // reason code, 0 = stays on this tier
+    if (!defer) {
+      const int64_t* ts_s = a.ts + row0;
+      const double* val_s = a.val + row0;
+      double* out_p = a.out + (size_t)s * (size_t)T + lane;
+      uint32_t* vw_p = a.valid + (size_t)s * a.Tw;
+      LeanState st;
+      st.j_cnt = 0; st.base_lo = 0; st.base_hi = -1; st.d_lo = 0; st.d_hi = 32; st.phase = 0;
+      uint32_t te = te_lane0;                                      // window end of step k_next + lane
+      uint32_t te31 = (uint32_t)a.range + 31u * (uint32_t)a.interval;  // ... of step k_next + 31
+      __syncwarp();
+      if (lane == 0) acc.put(0xffffffffu, 0u, -__longlong_as_double(0x7ff0000000000000ll));  // slot -1: (0, -inf)
+
+      // rows in 64-row blocks, lane holds rows j+lane and j+32+lane, prefetched one block ahead
+      const long long* p_t = reinterpret_cast<const long long*>(ts_s) + lane;
+      const double* p_v = val_s + lane;
+      long long t0 = 0, t1 = 0;
+      double v0 = 0.0, v1 = 0.0;  // lanes past the end keep a stale (already checked) value
+      if ((uint32_t)lane < n) { t0 = __ldcs(p_t); v0 = __ldcs(p_v); }
+      if ((uint32_t)lane + 32u < n) { t1 = __ldcs(p_t + 32); v1 = __ldcs(p_v + 32); }
+      while (st.j_cnt < n) {
+        const uint32_t j0 = st.j_cnt;  // multiple of 64
+        const long long c_t0 = t0, c_t1 = t1;
+        const double c_v0 = v0, c_v1 = v1;
+        const uint32_t left = n - j0;
+        const bool in0 = (uint32_t)lane < left, in1 = (uint32_t)lane + 32u < left;
+        if ((uint32_t)lane + 64u < left) { t0 = __ldcs(p_t + 64); v0 = __ldcs(p_v + 64); }
+        if ((uint32_t)lane + 96u < left) { t1 = __ldcs(p_t + 96); v1 = __ldcs(p_v + 96); }
+        p_t += 64;
+        p_v += 64;
+        // SeriesNormalize (offset bias) + 32-bit time domain, append to the ring: the block occupies slots
+        // (j0 mod RING) + [0, 64), which never wrap, and their mirrors RING further
+        const uint32_t slot = (j0 & (uint32_t)(RING - 1)) + (uint32_t)lane;
+        uint32_t* const pt = rts + slot;
+        double* const pv = rval + slot;
+        {
+          const long long d = c_t0 - tb_off;
+          const int32_t dh = (int32_t)(d >> 32);
+          const uint32_t dl = (uint32_t)d;
+          const uint32_t in = dl < a.rel_max ? dl : a.rel_max;
+          const uint32_t r = dh == 0 ? in : (dh < 0 ? 0u : a.rel_max);
+          if (in0) { pt[0] = r; pt[RING] = r; pv[0] = c_v0; pv[RING] = c_v0; }
+        }
+        {
+          const long long d = c_t1 - tb_off;
+          const int32_t dh = (int32_t)(d >> 32);
+          const uint32_t dl = (uint32_t)d;
+          const uint32_t in = dl < a.rel_max ? dl : a.rel_max;
+          const uint32_t r = dh == 0 ? in : (dh < 0 ? 0u : a.rel_max);
+          if (in1) { pt[32] = r; pt[32 + RING] = r; pv[32] = c_v1; pv[32 + RING] = c_v1; }
+        }
+        __syncwarp();
+        bool bad = (a.filter_nan != 0) & (isnan(c_v0) | isnan(c_v1));
+        if constexpr (TR::kCounter) {
+          // predecessor of the lane's first row through the mirror (slot-1+RING never wraps); slot -1 of a
+          // series holds -inf, so its first sample never counts as a reset
+          const double p0 = pv[RING - 1];
+          const double p1 = pv[31];
+          bad = bad | (in0 & (c_v0 < p0)) | (in1 & (c_v1 < p1));
+        }
+        if (__any_sync(0xffffffffu, bad)) { defer = 4; break; }
+        st.j_cnt = j0 + (left < 64u ? left : 64u);
+        const uint32_t t_new = acc.tm(st.j_cnt - 1u);
+        // every group whose last window end is older than the newest sample is final
+        while (te31 < t_new) {
+          if (B2P_LEAN_PAIR && te31 + step32 < t_new && lean_pair<FN>(a, st, acc, te, step32, out_p, vw_p, lane)) {
+            te += 2u * step32;
+            te31 += 2u * step32;
+            out_p += 64;
+            vw_p += 2;
+            continue;
+          }
+          if ((defer = lean_group<FN, false>(a, st, acc, n, te, 0, 0, out_p, vw_p, lane))) break;
+          te += step32;
+          te31 += step32;
+          out_p += 32;
+          vw_p += 1;
+        }
+        if (defer) break;
+        // a sample past the last window end: every remaining step is final and the rest of the series cannot
+        // reach a window any more; it still has to be free of NaN samples (SeriesNormalize would drop them and
+        // change the sample count m the cursor starts were compared with)
+        if (t_new >= a.rel_max) {
+          if (a.filter_nan) {
+            bool nan_left = false;
+            for (uint32_t j = st.j_cnt + (uint32_t)lane; j < n; j += 32u) nan_left = nan_left | isnan(val_s[j]);
+            if (__any_sync(0xffffffffu, nan_left)) defer = 6;
+          }
+          break;
+        }
+        // nothing seen so far can be inside a window that is still to come (history before the query): restart
+        // both edges behind it.  Only before the first non-empty window, where last_range_start is still 0.
+        if (st.phase == 0u && t_new <= te31 - te31_minus_tlo0) {
+          st.base_lo = st.j_cnt;
+          st.base_hi = (int32_t)st.j_cnt - 1;
+        }
+        // room for the next block (and the end sentinel) behind the oldest sample a window may still need
+        if (st.j_cnt + 66u - st.base_lo > (uint32_t)RING) { defer = 5; break; }
+      }
+      if (!defer) {
+        // ---- end of stream: sentinel, end trim (range_manipulate.rs:722-728), remaining groups -------
+        if (lane == 0) acc.put(st.j_cnt, 0xffffffffu, 0.0);
+        __syncwarp();
+        int32_t kl = T - 1;
+        {
+          const int64_t d = ts_s[n - 1u] - tb_off;  // newest sample, ms since start - range
+          if (d < 0) {
+            kl = -1;  // every sample is older than every window
+          } else if (d < (int64_t)a.rel_max) {
+            // last_aligned = trunc((last_ts + range) / interval) * interval, aligned to 0 (not to start);
+            // last_ts + range = start + d, so (last_ts + range) mod interval = (start_mod + d) mod interval
+            const uint32_t iv = (uint32_t)a.interval;
+            const uint32_t x = a.start_mod + (uint32_t)d;
+            const uint32_t xm = x % iv;
+            kl = ((uint32_t)d >= xm) ? (int32_t)(((uint32_t)d - xm) / iv) : -1;
+            kl = kl > T - 1 ? T - 1 : kl;
+          }
+        }
+        for (int32_t k_next = (int32_t)(out_p - (a.out + (size_t)s * (size_t)T + lane)); k_next < T; k_next += 32) {
+          if ((defer = lean_group<FN, true>(a, st, acc, n, te, k_next + lane, kl, out_p, vw_p, lane))) break;
+          te += step32;
+          out_p += 32;
+          vw_p += 1;
+        }
+      }
+    }
+    if (defer && lane == 0) {
+#ifdef B2P_LEAN_DEBUG
+      printf("lean: series %u leaves the tier, reason %d\n", s, defer);
+#endif
+      const uint32_t i = atomicAdd(&a.status->w_count, 1u);
+      a.w_list[i] = s;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace b2p

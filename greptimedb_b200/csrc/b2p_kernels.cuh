@@ -47,6 +47,7 @@ struct RangeArgs {
   double rcp_rs;     // RN(1/(range/1000)) when the Markstein division is exact for it, else 0
   double range_secs; // (double)range / 1000.0
   double rcp_interval; // 1.0 / interval
+  uint32_t start_mod;  // start mod interval (lean tier's end trim; valid when start >= 0)
   // input
   const int64_t* ts;
   const double* val;
@@ -655,9 +656,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_
       B2P_RUN_STEPS(T, kl);
       // cursor-overshoot quirk possible -> exact slow path decides
       if (!defer && st.j_cnt > 0 && st.max_c0 >= st.j_cnt) defer = true;
-      // "ignore this if all ranges are empty" (range_manipulate.rs:641-643): absent_over_time is the only
-      // function that yields Some on an empty window, so it alone needs the series-level veto.
-      if (FN == B2P_FN_ABSENT_OVER_TIME && !defer && !st.any_nonempty) {
+      // "ignore this if all ranges are empty" (range_manipulate.rs:641-643): only the functions that yield
+      // Some on an empty window (absent_over_time, quantile_over_time, holt_winters) need the series-level veto.
+      if (FnTraits<FN>::kSomeOnEmpty && !defer && !st.any_nonempty) {
         for (int32_t k = lane; k < T; k += 32) out_s[k] = 0.0;
         for (uint32_t w = lane; w < a.Tw; w += 32) vw_s[w] = 0u;
       }

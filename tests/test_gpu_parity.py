@@ -315,13 +315,30 @@ def ctx_thread_tier():
     c.close()
 
 
+@pytest.fixture(scope="module")
+def ctx_no_lean():
+    """A context with the lean first tier (K2L) switched off: rate / increase / delta go straight to K2."""
+    import os
+    from greptimedb_b200 import Context
+    os.environ["B2P_DISABLE_LEAN_TIER"] = "1"
+    try:
+        c = Context(0)
+    finally:
+        del os.environ["B2P_DISABLE_LEAN_TIER"]
+    yield c
+    c.close()
+
+
 RATE_EXACT_SHAPES = ((1000, 1, 300_000), (0, 0, 300_000), (977, 1, 77_777), (1000, 0, 1_000_000))
 
 
-def test_rate_warp_tier_is_bit_exact_against_the_rescan_oracle(ctx):
-    """Warp-per-series kernel: the two-FMA divisions (by window length, by range seconds) must round exactly
-    like IEEE division, and the bitmask reset correction must add exactly what the reference's rescan adds."""
+@pytest.mark.parametrize("lean", [True, False])
+def test_rate_warp_tier_is_bit_exact_against_the_rescan_oracle(ctx, ctx_no_lean, lean):
+    """Warp-per-series kernels (lean tier + K2, or K2 alone): the two-FMA divisions (by window length, by range
+    seconds) must round exactly like IEEE division, and the bitmask reset correction must add exactly what the
+    reference's rescan adds."""
     from greptimedb_b200 import make_params
+    ctx = ctx if lean else ctx_no_lean
     S, N, T0 = 256, 1000, 1_700_000_000_000
     for jitter, resets, rng_ms in RATE_EXACT_SHAPES:
         ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, jitter, resets, 0x5EED)
@@ -358,6 +375,51 @@ def test_rate_thread_tier_is_bit_exact_against_the_reference_sliding_path(ctx_th
                 assert (valid == e_valid).all(), (fn, jitter, resets, rng_ms, interval)
                 assert (out.view(np.uint64) == e_out.view(np.uint64)).all(), (fn, jitter, resets, rng_ms, interval)
                 assert ctx.last_slow_series() == 0
+
+
+def test_lean_tier_keeps_regular_series_and_hands_off_the_rest(ctx, ctx_no_lean):
+    """K2L evaluates every series of the BASELINE shape itself (no hand-off) and is bit-identical to K2 alone; series
+    with counter resets or NaN samples, sparse step grids and windows longer than its ring go to K2 and still match."""
+    from greptimedb_b200 import make_params
+    S, N, T0 = 512, 1000, 1_700_000_000_000
+    offsets = np.arange(S + 1, dtype=np.uint64) * N
+    for fn in ("rate", "increase", "delta"):
+        for jitter, resets, start, end, interval, rng_ms, all_lean in (
+                (1000, 0, T0, T0 + 999 * 15_000, 15_000, 300_000, True),          # BASELINE config 2
+                (0, 0, T0 + 7, T0 + 999 * 15_000 + 100_000, 15_000, 300_000, True),  # steps off the scrape grid, past the data
+                (1000, 0, T0 - 600_000, T0 + 500 * 15_000, 5_000, 60_000, True),   # leading empty windows, 3 steps per sample
+                (1000, 0, T0 + 3_000_000, T0 + 6_000_000, 45_000, 300_000, True),  # history before the query: clamped samples
+                (1000, 1, T0, T0 + 999 * 15_000, 15_000, 300_000, fn == "delta"),  # counter resets: hand-off (not for delta)
+                (1000, 0, T0, T0 + 999 * 15_000, 300_000, 300_000, False),         # 20 samples per step: ring pressure
+                (1000, 0, T0, T0 + 999 * 15_000, 15_000, 6_000_000, False)):       # 400-sample windows
+            ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, jitter, resets, 0x5EED)
+            p = make_params(fn, start, end, interval, rng_ms)
+            out, valid, ets = ctx.range_eval_n(p, ts, val, sid, None, S)
+            handed = ctx.last_warp_tier_series()
+            out2, valid2, _ = ctx_no_lean.range_eval_n(p, ts, val, sid, None, S)
+            vb, vb2 = orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(valid2, ets.size)
+            tag = (fn, jitter, resets, start - T0, interval, rng_ms)
+            assert (vb == vb2).all(), tag
+            assert (out.view(np.uint64)[vb] == out2.view(np.uint64)[vb]).all(), tag
+            op = orc.make_params(fn, start, end, interval, rng_ms)
+            e_out, e_valid = orc.range_query(op, ts, val, sid, offsets, threads=4)
+            assert_close(out, e_out, vb, orc.valid_to_bool(e_valid, ets.size), f"lean tier {tag}")
+            if all_lean:
+                # a sample exactly on an eval step next to the series' end can make calculate_range's cursor
+                # overshoot (DESIGN.md C-13); those few series rightly go on to K2 and the exact slow kernel
+                assert handed <= S // 64, (tag, handed)
+            else:
+                assert handed > 0, tag
+    # NaN samples (SeriesNormalize drops them): those series leave the tier, the others stay
+    ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, 1000, 0, 0x5EED)
+    val = val.copy()
+    val.reshape(S, N)[::4, 500] = np.nan
+    p = make_params("rate", T0, T0 + 999 * 15_000, 15_000, 300_000)
+    out, valid, ets = ctx.range_eval_n(p, ts, val, sid, None, S)
+    assert S // 4 <= ctx.last_warp_tier_series() <= S // 4 + S // 64
+    op = orc.make_params("rate", T0, T0 + 999 * 15_000, 15_000, 300_000)
+    e_out, e_valid = orc.range_query(op, ts, val, sid, offsets, threads=4)
+    assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size), "lean tier NaN hand-off")
 
 
 def test_thread_tier_hands_off_what_it_cannot_do(ctx_thread_tier):
@@ -598,7 +660,7 @@ def _fuzz_series(rng, n_series):
 
 
 @pytest.mark.parametrize("seed", range(12))
-def test_fuzz_random_queries_match_oracle(ctx, ctx_thread_tier, seed):
+def test_fuzz_random_queries_match_oracle(ctx, ctx_thread_tier, ctx_no_lean, seed):
     """Random series zoo x random (start, end, interval, range, offset): validity bit-exact, values <= 1e-9 rel."""
     from greptimedb_b200 import make_params
     rng = np.random.default_rng(1000 + seed)
@@ -616,7 +678,7 @@ def test_fuzz_random_queries_match_oracle(ctx, ctx_thread_tier, seed):
             p = make_params(fn, start, end, interval, rng_ms, offset=offset, param0=0.75)
             op = orc.make_params(fn, start, end, interval, rng_ms, offset=offset, param0=0.75)
             e_out, e_valid = orc.range_query(op, ts, val, None, offsets)
-            for c in ((ctx, ctx_thread_tier) if fn in ("rate", "increase", "delta") else (ctx,)):
+            for c in ((ctx, ctx_thread_tier, ctx_no_lean) if fn in ("rate", "increase", "delta") else (ctx,)):
                 out, valid, ets = c.range_eval(p, ts, val, offsets=offsets)
                 assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size),
                              f"fuzz seed={seed} {fn} start={start} end={end} int={interval} rng={rng_ms} off={offset}",
