@@ -90,7 +90,7 @@ struct b2p_ctx {
   bool thread_tier = false;
   // K2L, the lean warp-per-series tier in front of K2 (default on; B2P_DISABLE_LEAN_TIER=1 turns it off)
   bool lean_tier = true;
-  int lean_blocks_per_sm[3] = {0, 0, 0};
+  int lean_blocks_per_sm[B2P_FN__COUNT] = {};
   size_t arena_rows = 0;
   cudaEvent_t ev[4][2] = {};
   bool ev_used[4] = {false, false, false, false};
@@ -165,9 +165,22 @@ bool fits_ts32(const RangeArgs& a) {
   return span >= 0 && span < 2147483000.0 && a.interval < 2147483000ll && a.range < 2147483000ll;
 }
 
+template <int FN>
+constexpr bool lean_supports() { return LeanTraits<FN>::kSupported; }
+
+bool lean_fn_supported(int fn) {
+  switch (fn) {
+#define X(N) case N: return lean_supports<N>();
+    X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20)
+#undef X
+  }
+  return false;
+}
+
 bool lean_ok(const b2p_ctx* c, int fn, const RangeArgs& a) {
-  if (!c->lean_tier || !(fn == B2P_FN_RATE || fn == B2P_FN_INCREASE || fn == B2P_FN_DELTA)) return false;
-  if (!fits_ts32(a) || a.rcp_rs == 0.0 || a.range < a.interval || a.start < 0) return false;
+  if (!c->lean_tier || !lean_fn_supported(fn)) return false;
+  if (!fits_ts32(a) || a.range < a.interval || a.start < 0) return false;
+  if (fn == B2P_FN_RATE && a.rcp_rs == 0.0) return false;
   return (double)a.rel_max + 64.0 * (double)a.interval < 4294967295.0;
 }
 
@@ -184,7 +197,7 @@ bool lean_ok(const b2p_ctx* c, int fn, const RangeArgs& a);
 
 template <int FN>
 int launch_lean(b2p_ctx* c, const RangeArgs& a) {
-  constexpr size_t smem = (size_t)kWarpsPerCta * 2 * kLeanRing * 12 + kRcpTable * 8;
+  constexpr size_t smem = (size_t)kWarpsPerCta * kLeanRing * 16 + kRcpTable * 8 + (size_t)kWarpsPerCta * 2 * 64 * 16;
   auto kern = range_lean_kernel<FN>;
   int& cached = c->lean_blocks_per_sm[FN];
   if (cached == 0) {
@@ -201,6 +214,23 @@ int launch_lean(b2p_ctx* c, const RangeArgs& a) {
   c->launches++;
   CU(cudaGetLastError());
   return B2P_OK;
+}
+
+template <int FN>
+int launch_lean_if_supported(b2p_ctx* c, const RangeArgs& a) {
+  if constexpr (LeanTraits<FN>::kSupported)
+    return launch_lean<FN>(c, a);
+  else
+    return fail(B2P_E_INVALID, "fn_id %d has no lean tier", FN);
+}
+
+int dispatch_lean(b2p_ctx* c, int fn, const RangeArgs& a) {
+  switch (fn) {
+#define X(N) case N: return launch_lean_if_supported<N>(c, a);
+    X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20)
+#undef X
+  }
+  return fail(B2P_E_INVALID, "unknown fn_id %d", fn);
 }
 
 template <int FN>
@@ -463,7 +493,7 @@ static int series_offsets_impl(b2p_ctx* c, const uint32_t* sid, uint64_t n_rows,
   if (!c || !offsets || (!sid && n_rows)) return fail(B2P_E_INVALID, "NULL argument");
   if (!aligned16(sid)) return fail(B2P_E_INVALID, "sid must be 16-byte aligned");
   DeviceGuard g(c->device);
-  uint64_t blocks = (n_rows / 8 + 255) / 256;
+  uint64_t blocks = (n_rows / 16 + 255) / 256;
   const uint64_t cap = (uint64_t)c->num_sms * 16;
   if (blocks > cap) blocks = cap;
   if (blocks == 0) blocks = 1;
@@ -529,10 +559,7 @@ int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts,
     if (rc) return rc;
     a.use_w_list = 1;
   } else if (lean_ok(c, p->fn_id, a)) {
-    if (p->fn_id == B2P_FN_RATE) rc = launch_lean<B2P_FN_RATE>(c, a);
-    else if (p->fn_id == B2P_FN_INCREASE) rc = launch_lean<B2P_FN_INCREASE>(c, a);
-    else rc = launch_lean<B2P_FN_DELTA>(c, a);
-    if (rc) return rc;
+    if ((rc = dispatch_lean(c, p->fn_id, a))) return rc;
     a.use_w_list = 1;
   }
   rc = dispatch_fast(c, p->fn_id, a);

@@ -33,6 +33,51 @@ namespace b2p {
 #endif
 constexpr int kLeanRing = 256;
 
+// The per-warp sample ring of this tier.  Timestamps (uint32 ms since start - range) are stored twice, slot p
+// and slot p + RING, so the edge reads around an index need no wrap handling after set_window(); values are
+// stored once and read through a mask (two reads per step), which keeps four CTAs per SM inside shared memory.
+struct LeanRing {
+  using time_type = uint32_t;
+  static constexpr int RING = kLeanRing;
+  static constexpr bool kHasFlags = false;  // series with counter resets leave the tier; resets()/changes() never enter
+  static constexpr bool kHasRcp = true;
+  uint32_t* ts;            // [2*RING]
+  double* val;             // [RING]
+  const double* rcp_tab;   // [kRcpTable] RN(1/n)
+  const uint32_t* ts_lin;  // ts + (j0 & (RING-1)) - j0
+  __device__ __forceinline__ void set_window(int32_t j0) { ts_lin = ts + ((j0 & (RING - 1)) - j0); }
+  __device__ __forceinline__ void put(uint32_t j, uint32_t t, double v) {
+    const uint32_t p = j & (RING - 1);
+    ts[p] = t;
+    ts[p + RING] = t;
+    val[p] = v;
+  }
+  __device__ __forceinline__ uint32_t t(uint32_t j) const { return ts_lin[(int32_t)j]; }
+  __device__ __forceinline__ uint32_t tm(uint32_t j) const { return ts[j & (RING - 1)]; }
+  __device__ __forceinline__ double v(uint32_t j) const { return val[j & (RING - 1)]; }
+  __device__ __forceinline__ double rcp(uint32_t n) const { return rcp_tab[n]; }
+  __device__ __forceinline__ uint32_t fw(uint32_t) const { return 0u; }
+};
+
+// Range functions this tier evaluates: everything whose value only depends on the window's samples and that is
+// null on an empty window.  resets()/changes() need the reset/change bit words of the second tier; absent_over_time,
+// quantile_over_time and holt_winters yield a value on an EMPTY window, which needs the series-level veto
+// (range_manipulate.rs:641-643) the second tier implements.
+template <int FN>
+struct LeanTraits {
+  static constexpr bool kSupported = !(FN == B2P_FN_RESETS || FN == B2P_FN_CHANGES || FnTraits<FN>::kSomeOnEmpty);
+};
+
+// 8-byte asynchronous global -> shared copy (LDGSTS): the next block's rows land in a per-warp staging area
+// without passing through registers.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct LeanState {  // warp-uniform
   uint32_t j_cnt;    // samples in the ring's ordinal space (== rows consumed: nothing is filtered on this tier)
   uint32_t base_lo;  // window start of the last evaluated step (in phase 1 also calculate_range's last_range_start)
@@ -44,10 +89,33 @@ struct LeanState {  // warp-uniform
   uint32_t phase;
 };
 
+// The value of one step whose window [q, g] (both edge timestamps known) is already established.
+template <int FN>
+__device__ __forceinline__ double lean_value(const RangeArgs& a, const LeanRing& acc, int32_t g, uint32_t q,
+                                             uint32_t t_lo, uint32_t t_hi, uint32_t te, bool& ok) {
+  const uint32_t l = (uint32_t)(g + 1) - q;  // 0 for an empty window (q == g + 1)
+  double r = 0.0;
+  if constexpr (FnTraits<FN>::kExtrapolated) {
+    ok = (int32_t)l >= 2;
+    if (ok) {
+      const double first_value = acc.v(q);
+      const double last_value = acc.v((uint32_t)g);
+      // counters add the reset correction, 0.0 on this tier (keeps the sign of a zero difference identical)
+      const double result_value = FnTraits<FN>::kCounter ? (last_value - first_value) + 0.0 : last_value - first_value;
+      r = extrapolate_parts<FN, uint32_t, true>(result_value, first_value, t_lo, t_hi, l, te, (uint32_t)a.range,
+                                                acc.rcp(l - 1u), a.range_secs, a.rcp_rs);
+    }
+  } else {
+    ok = eval_window<FN>(acc, q, l, te, (uint32_t)a.range, a.p0, a.p1, a.rcp_rs, r);
+    if (!ok) r = 0.0;
+  }
+  return r;
+}
+
 // One aligned group of 32 steps; lane's step is k (window end te, start tlo = te - range, both in the 32-bit
 // domain).  Returns 0, or the reason (> 0) why the series has to go to the second tier.
 template <int FN, bool TAIL>
-__device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, RingAcc<kLeanRing, true>& acc,
+__device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, LeanRing& acc,
                                            uint32_t m, uint32_t te, int32_t k, int32_t kl, double* out_p,
                                            uint32_t* vw_p, int lane) {
   const uint32_t rng = (uint32_t)a.range;
@@ -78,6 +146,7 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Rin
     st.base_hi += (int32_t)st.d_hi;
     st.base_lo += st.d_lo;
   } else {
+    const bool lead = st.phase == 0u;
     // some guess missed (or the state is not the steady one): every lane walks to the definitional edges;
     // the sentinels bound all four walks
     while (acc.t((uint32_t)(g + 1)) <= te) ++g;
@@ -111,21 +180,17 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Rin
     const int32_t nhi = __shfl_sync(0xffffffffu, g, 31);
     const uint32_t nlo = __shfl_sync(0xffffffffu, q, 31);
     st.d_hi = (uint32_t)(nhi - st.base_hi);
-    st.d_lo = nlo - st.base_lo;
+    // the group that holds the first non-empty window ramps up (its window starts do not move until a window is
+    // full): in the steady state that follows both edges advance at the same rate, so guess that instead
+    st.d_lo = lead ? st.d_hi : nlo - st.base_lo;
     st.base_hi = nhi;
     st.base_lo = nlo;
   }
-  const uint32_t l = (uint32_t)(g + 1) - q;  // 0 for an empty window (q == g + 1)
-  bool ok = (int32_t)l >= 2;
-  if (TAIL) ok = ok && (k <= kl);
-  double r = 0.0;
-  if (ok) {
-    const double first_value = acc.v(q);
-    const double last_value = acc.v((uint32_t)g);
-    // counters add the reset correction, 0.0 on this tier (keeps the sign of a zero difference identical)
-    const double result_value = FnTraits<FN>::kCounter ? (last_value - first_value) + 0.0 : last_value - first_value;
-    r = extrapolate_parts<FN, uint32_t, true>(result_value, first_value, t_lo, t_hi, l, te, rng,
-                                              acc.rcp(l - 1u), a.range_secs, a.rcp_rs);
+  bool ok;
+  double r = lean_value<FN>(a, acc, g, q, t_lo, t_hi, te, ok);
+  if (TAIL && k > kl) {  // trimmed by RangeManipulate's end alignment
+    ok = false;
+    r = 0.0;
   }
   if (!TAIL || k < (int32_t)a.T) *out_p = r;
   const uint32_t vw = __ballot_sync(0xffffffffu, ok);
@@ -138,29 +203,12 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Rin
 #define B2P_LEAN_PAIR 1
 #endif
 
-// The value of one step whose window [q, g] (both edge timestamps known) has already been verified.
-template <int FN>
-__device__ __forceinline__ double lean_value(const RangeArgs& a, const RingAcc<kLeanRing, true>& acc, int32_t g,
-                                             uint32_t q, uint32_t t_lo, uint32_t t_hi, uint32_t te, bool& ok) {
-  const uint32_t l = (uint32_t)(g + 1) - q;
-  ok = (int32_t)l >= 2;
-  double r = 0.0;
-  if (ok) {
-    const double first_value = acc.v(q);
-    const double last_value = acc.v((uint32_t)g);
-    const double result_value = FnTraits<FN>::kCounter ? (last_value - first_value) + 0.0 : last_value - first_value;
-    r = extrapolate_parts<FN, uint32_t, true>(result_value, first_value, t_lo, t_hi, l, te, (uint32_t)a.range,
-                                              acc.rcp(l - 1u), a.range_secs, a.rcp_rs);
-  }
-  return r;
-}
-
 // Two consecutive groups (64 steps) in one go, steady state only: before the end of the stream, previous step
 // non-empty, at most one sample of advance per step (so no cursor start can reach m, see lean_group), and every
 // one of the 64 proportional guesses verified by one vote.  Returns false without side effects when any of that
 // does not hold; the caller then takes the groups one at a time.
 template <int FN>
-__device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, RingAcc<kLeanRing, true>& acc, uint32_t te,
+__device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, LeanRing& acc, uint32_t te,
                                           uint32_t step32, double* out_p, uint32_t* vw_p, int lane) {
   const int32_t top = (int32_t)st.j_cnt - 1;
   // uniform gates; the last two keep every read below the newest sample (slot top), i.e. on written slots
@@ -201,13 +249,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
   using TR = FnTraits<FN>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // smem: [warps][2*RING] val f64 | [warps][2*RING] ts u32 | [kRcpTable] f64
-  double* rval = reinterpret_cast<double*>(smem_raw) + warp * (2 * RING);
-  uint32_t* rts = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kWarpsPerCta * 2 * RING * 8) + warp * (2 * RING);
-  double* rcp_tab = reinterpret_cast<double*>(smem_raw + (size_t)kWarpsPerCta * 2 * RING * 12);
+  // smem: [warps][RING] val f64 | [warps][2*RING] ts u32 | [kRcpTable] f64 | [warps][2][64] ts i64 |
+  //       [warps][2][64] val f64 (staging of the block being fetched and the block being consumed)
+  double* rval = reinterpret_cast<double*>(smem_raw) + warp * RING;
+  uint32_t* rts = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kWarpsPerCta * RING * 8) + warp * (2 * RING);
+  double* rcp_tab = reinterpret_cast<double*>(smem_raw + (size_t)kWarpsPerCta * RING * 16);
+  long long* const stage_t = reinterpret_cast<long long*>(rcp_tab + kRcpTable) + warp * 128 + lane;
+  double* const stage_v = reinterpret_cast<double*>(rcp_tab + kRcpTable) + kWarpsPerCta * 128 + warp * 128 + lane;
   for (int i = threadIdx.x; i < kRcpTable; i += blockDim.x) rcp_tab[i] = (i > 0) ? 1.0 / (double)i : 0.0;
   __syncthreads();
-  RingAcc<RING, true> acc{rts, rval, nullptr, rcp_tab, rts, rval, true};
+  LeanRing acc{rts, rval, rcp_tab, rts};
   const uint32_t total_warps = gridDim.x * kWarpsPerCta;
   const int32_t T = (int32_t)a.T;
   const long long tb_off = a.tb - a.offset;  // rel = ts + offset - tb
@@ -231,23 +282,31 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
       __syncwarp();
       if (lane == 0) acc.put(0xffffffffu, 0u, -__longlong_as_double(0x7ff0000000000000ll));  // slot -1: (0, -inf)
 
-      // rows in 64-row blocks, lane holds rows j+lane and j+32+lane, prefetched one block ahead
+      // rows in 64-row blocks, lane owns rows j+lane and j+32+lane; the block after the one being consumed is
+      // in flight into the other half of the staging area (cp.async, one commit group per block)
       const long long* p_t = reinterpret_cast<const long long*>(ts_s) + lane;
       const double* p_v = val_s + lane;
-      long long t0 = 0, t1 = 0;
-      double v0 = 0.0, v1 = 0.0;  // lanes past the end keep a stale (already checked) value
-      if ((uint32_t)lane < n) { t0 = __ldcs(p_t); v0 = __ldcs(p_v); }
-      if ((uint32_t)lane + 32u < n) { t1 = __ldcs(p_t + 32); v1 = __ldcs(p_v + 32); }
+      cp_async_wait<0>();  // a series that left the tier early may still have a block in flight into the staging area
+      if ((uint32_t)lane < n) { cp_async8(stage_t, p_t); cp_async8(stage_v, p_v); }
+      if ((uint32_t)lane + 32u < n) { cp_async8(stage_t + 32, p_t + 32); cp_async8(stage_v + 32, p_v + 32); }
+      cp_async_commit();
+      uint32_t half = 0;  // staging half (in elements) of the block being consumed
       while (st.j_cnt < n) {
         const uint32_t j0 = st.j_cnt;  // multiple of 64
-        const long long c_t0 = t0, c_t1 = t1;
-        const double c_v0 = v0, c_v1 = v1;
         const uint32_t left = n - j0;
         const bool in0 = (uint32_t)lane < left, in1 = (uint32_t)lane + 32u < left;
-        if ((uint32_t)lane + 64u < left) { t0 = __ldcs(p_t + 64); v0 = __ldcs(p_v + 64); }
-        if ((uint32_t)lane + 96u < left) { t1 = __ldcs(p_t + 96); v1 = __ldcs(p_v + 96); }
-        p_t += 64;
-        p_v += 64;
+        {
+          const uint32_t other = half ^ 64u;
+          if ((uint32_t)lane + 64u < left) { cp_async8(stage_t + other, p_t + 64); cp_async8(stage_v + other, p_v + 64); }
+          if ((uint32_t)lane + 96u < left) { cp_async8(stage_t + other + 32, p_t + 96); cp_async8(stage_v + other + 32, p_v + 96); }
+          cp_async_commit();
+          p_t += 64;
+          p_v += 64;
+        }
+        cp_async_wait<1>();  // everything but the newest group: the block to consume has landed
+        const long long c_t0 = stage_t[half], c_t1 = stage_t[half + 32];
+        const double c_v0 = stage_v[half], c_v1 = stage_v[half + 32];
+        half ^= 64u;
         // SeriesNormalize (offset bias) + 32-bit time domain, append to the ring: the block occupies slots
         // (j0 mod RING) + [0, 64), which never wrap, and their mirrors RING further
         const uint32_t slot = (j0 & (uint32_t)(RING - 1)) + (uint32_t)lane;
@@ -259,7 +318,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
           const uint32_t dl = (uint32_t)d;
           const uint32_t in = dl < a.rel_max ? dl : a.rel_max;
           const uint32_t r = dh == 0 ? in : (dh < 0 ? 0u : a.rel_max);
-          if (in0) { pt[0] = r; pt[RING] = r; pv[0] = c_v0; pv[RING] = c_v0; }
+          if (in0) { pt[0] = r; pt[RING] = r; pv[0] = c_v0; }
         }
         {
           const long long d = c_t1 - tb_off;
@@ -267,14 +326,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
           const uint32_t dl = (uint32_t)d;
           const uint32_t in = dl < a.rel_max ? dl : a.rel_max;
           const uint32_t r = dh == 0 ? in : (dh < 0 ? 0u : a.rel_max);
-          if (in1) { pt[32] = r; pt[32 + RING] = r; pv[32] = c_v1; pv[32 + RING] = c_v1; }
+          if (in1) { pt[32] = r; pt[32 + RING] = r; pv[32] = c_v1; }
         }
         __syncwarp();
-        bool bad = (a.filter_nan != 0) & (isnan(c_v0) | isnan(c_v1));
+        bool bad = (a.filter_nan != 0) & ((in0 & isnan(c_v0)) | (in1 & isnan(c_v1)));
         if constexpr (TR::kCounter) {
-          // predecessor of the lane's first row through the mirror (slot-1+RING never wraps); slot -1 of a
-          // series holds -inf, so its first sample never counts as a reset
-          const double p0 = pv[RING - 1];
+          // slot -1 of a series holds -inf, so its first sample never counts as a reset
+          const double p0 = rval[(slot - 1u) & (uint32_t)(RING - 1)];
           const double p1 = pv[31];
           bad = bad | (in0 & (c_v0 < p0)) | (in1 & (c_v1 < p1));
         }

@@ -83,58 +83,81 @@ __device__ __forceinline__ int64_t rem_euclid(int64_t a, int64_t b) {
 // Replaces find_first_diff_row's row-by-row tag compare (series_divide.rs:622-670); ids must be
 // non-decreasing (the reference requires the same ordering, series_divide.rs:410-440).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void offsets_scan(const uint32_t* v, int cnt, uint32_t prev, uint64_t r0, uint64_t n_rows,
-                                             uint32_t n_series, uint64_t* __restrict__ offsets, Status* status) {
-  for (int i = 0; i < cnt; ++i) {
-    const uint64_t r = r0 + i;
-    const uint32_t cur = v[i];
-    if (cur >= n_series) {
-      atomicOr(&status->k0_errors, 2u);
-    } else if (r == 0) {
-      for (uint32_t s = 0; s <= cur; ++s) offsets[s] = 0;
-    } else if (cur != prev) {
-      if (cur < prev)
-        atomicOr(&status->k0_errors, 1u);
-      else
-        for (uint32_t s = prev + 1; s <= cur; ++s) offsets[s] = r;
-    }
-    if (r == n_rows - 1 && cur < n_series)
-      for (uint32_t s = cur + 1; s <= n_series; ++s) offsets[s] = n_rows;
-    prev = cur;
+// One id of the scalar scan (row r holds id `cur`, the row before it `prev`).
+__device__ __forceinline__ void offsets_scan_one(uint32_t cur, uint32_t prev, uint64_t r, uint64_t n_rows,
+                                                 uint32_t n_series, uint64_t* __restrict__ offsets, Status* status) {
+  if (cur >= n_series) {
+    atomicOr(&status->k0_errors, 2u);
+  } else if (r == 0) {
+    for (uint32_t s = 0; s <= cur; ++s) offsets[s] = 0;
+  } else if (cur != prev) {
+    if (cur < prev)
+      atomicOr(&status->k0_errors, 1u);
+    else
+      for (uint32_t s = prev + 1; s <= cur; ++s) offsets[s] = r;
   }
+  if (r == n_rows - 1 && cur < n_series)
+    for (uint32_t s = cur + 1; s <= n_series; ++s) offsets[s] = n_rows;
 }
 
 __global__ void __launch_bounds__(256) series_offsets_kernel(const uint32_t* __restrict__ sid, uint64_t n_rows,
                                                              uint32_t n_series, uint32_t sid_base,
                                                              uint64_t* __restrict__ offsets, Status* status) {
-  // 8 ids per thread per iteration (two independent 128-bit loads in flight).  Almost every octet lies
-  // inside one series: a branch-free XOR/OR test against the preceding id skips it; only octets
-  // that contain a change (or the first / last row) take the scalar scan.
-  const uint64_t n8 = (n_rows + 7) / 8;
-  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n8; q += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t r0 = q * 8;
-    uint32_t v[8];
-    int cnt = 8;
-    if (r0 + 7 < n_rows) {
-      const uint4 x0 = __ldcs(reinterpret_cast<const uint4*>(sid + r0));
-      const uint4 x1 = __ldcs(reinterpret_cast<const uint4*>(sid + r0 + 4));
-      v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
-      v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-    } else {
-      cnt = (int)(n_rows - r0);
+  // A warp covers 512 consecutive ids per iteration: four independent 128-bit loads (4 ids each) per lane.
+  // The id before a lane's quad comes from its neighbour by shuffle (lane 0: from lane 31's previous quad, or
+  // one scalar read for the first).  Almost every quad lies inside one series: a branch-free XOR/OR test skips
+  // it; only quads that contain a change (or the first / last row) take the scalar scan.
+  constexpr int U = 4;
+  const int lane = threadIdx.x & 31;
+  const uint64_t nq = (n_rows + 3) / 4;
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t base = warp0 * (32 * U); base < nq; base += n_warps * (32 * U)) {
+    uint32_t v[U][4];
+    int cnt[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = (i < cnt) ? sid[r0 + i] : 0u;
+    for (int j = 0; j < U; ++j) {
+      const uint64_t r0 = (base + (uint64_t)j * 32 + lane) * 4;
+      v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0u;
+      cnt[j] = 0;
+      if (r0 + 3 < n_rows) {
+        const uint4 x = __ldcs(reinterpret_cast<const uint4*>(sid + r0));
+        v[j][0] = x.x; v[j][1] = x.y; v[j][2] = x.z; v[j][3] = x.w;
+        cnt[j] = 4;
+      } else if (r0 < n_rows) {
+        cnt[j] = (int)(n_rows - r0);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (i < cnt[j]) v[j][i] = sid[r0 + i];
+      }
     }
-    const uint32_t prev_raw = (r0 == 0) ? v[0] : sid[r0 - 1];
-    uint32_t diff = prev_raw ^ v[0];
+    uint32_t carry = 0u;  // lane 31's last id of the previous quad row
+    {
+      const uint64_t r0 = base * 4;
+      if (lane == 0 && r0 > 0 && r0 < n_rows) carry = sid[r0 - 1];
+    }
 #pragma unroll
-    for (int i = 1; i < 8; ++i) diff |= (i < cnt) ? (v[i - 1] ^ v[i]) : 0u;
-    const bool edge = (r0 == 0) || (r0 + 8 >= n_rows);
-    const bool in_range = (v[0] - sid_base) < n_series;  // no change => one check covers the octet
-    if (diff == 0u && !edge && in_range) continue;
+    for (int j = 0; j < U; ++j) {
+      const uint64_t r0 = (base + (uint64_t)j * 32 + lane) * 4;
+      uint32_t prev_raw = __shfl_up_sync(0xffffffffu, v[j][3], 1);
+      const uint32_t last = __shfl_sync(0xffffffffu, v[j][3], 31);
+      if (lane == 0) prev_raw = (r0 == 0) ? v[j][0] : carry;
+      carry = last;
+      if (cnt[j] == 0) continue;
+      uint32_t diff = prev_raw ^ v[j][0];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] -= sid_base;  // ids below sid_base wrap to >= n_series and are flagged
-    offsets_scan(v, cnt, prev_raw - sid_base, r0, n_rows, n_series, offsets, status);
+      for (int i = 1; i < 4; ++i) diff |= (i < cnt[j]) ? (v[j][i - 1] ^ v[j][i]) : 0u;
+      const bool edge = (r0 == 0) || (r0 + 4 >= n_rows);
+      const bool in_range = (v[j][0] - sid_base) < n_series;  // no change => one check covers the quad
+      if (diff == 0u && !edge && in_range) continue;
+      uint32_t prev = prev_raw - sid_base;  // ids below sid_base wrap to >= n_series and are flagged
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t cur = v[j][i] - sid_base;
+        if (i < cnt[j]) offsets_scan_one(cur, prev, r0 + i, n_rows, n_series, offsets, status);
+        prev = cur;
+      }
+    }
   }
   if (n_rows == 0 && blockIdx.x == 0)
     for (uint32_t s = threadIdx.x; s <= n_series; s += blockDim.x) offsets[s] = 0;
