@@ -44,18 +44,37 @@ struct LeanRing {
   uint32_t* ts;            // [2*RING]
   double* val;             // [RING]
   const double* rcp_tab;   // [kRcpTable] RN(1/n)
-  const uint32_t* ts_lin;  // ts + (j0 & (RING-1)) - j0
-  __device__ __forceinline__ void set_window(int32_t j0) { ts_lin = ts + ((j0 & (RING - 1)) - j0); }
+  // the same three arrays as 32-bit shared-space byte addresses: the hot reads go through ld.shared with a plain
+  // register base (a generic pointer makes the compiler rebuild the shared window base around every use)
+  uint32_t ts_sa, val_sa, rcp_sa;
+  uint32_t lin_sa;         // ts_sa + 4 * ((j0 & (RING-1)) - j0)
+  __device__ __forceinline__ void init_addresses() {
+    ts_sa = (uint32_t)__cvta_generic_to_shared(ts);
+    val_sa = (uint32_t)__cvta_generic_to_shared(val);
+    rcp_sa = (uint32_t)__cvta_generic_to_shared(rcp_tab);
+    lin_sa = ts_sa;
+  }
+  static __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t x;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(addr) : "memory");
+    return x;
+  }
+  static __device__ __forceinline__ double lds64(uint32_t addr) {
+    double x;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(addr) : "memory");
+    return x;
+  }
+  __device__ __forceinline__ void set_window(int32_t j0) { lin_sa = ts_sa + (uint32_t)(((j0 & (RING - 1)) - j0) << 2); }
   __device__ __forceinline__ void put(uint32_t j, uint32_t t, double v) {
     const uint32_t p = j & (RING - 1);
     ts[p] = t;
     ts[p + RING] = t;
     val[p] = v;
   }
-  __device__ __forceinline__ uint32_t t(uint32_t j) const { return ts_lin[(int32_t)j]; }
-  __device__ __forceinline__ uint32_t tm(uint32_t j) const { return ts[j & (RING - 1)]; }
-  __device__ __forceinline__ double v(uint32_t j) const { return val[j & (RING - 1)]; }
-  __device__ __forceinline__ double rcp(uint32_t n) const { return rcp_tab[n]; }
+  __device__ __forceinline__ uint32_t t(uint32_t j) const { return lds32(lin_sa + (j << 2)); }
+  __device__ __forceinline__ uint32_t tm(uint32_t j) const { return lds32(ts_sa + ((j & (RING - 1)) << 2)); }
+  __device__ __forceinline__ double v(uint32_t j) const { return lds64(val_sa + ((j & (RING - 1)) << 3)); }
+  __device__ __forceinline__ double rcp(uint32_t n) const { return lds64(rcp_sa + (n << 3)); }
   __device__ __forceinline__ uint32_t fw(uint32_t) const { return 0u; }
 };
 
@@ -156,7 +175,9 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Lea
     while (acc.t(q) <= tlo) ++q;
     t_hi = acc.t((uint32_t)g);
     t_lo = acc.t(q);
-    const bool ne = (int32_t)q <= g;
+    // steps past the trimmed end (and past the grid) are never visited by calculate_range: for the cursor
+    // bookkeeping they count as empty
+    const bool ne = ((int32_t)q <= g) && (!TAIL || k <= kl);
     const uint32_t ne_mask = __ballot_sync(0xffffffffu, ne);
     // empty windows are only tolerated before the first and after the last non-empty one
     if (ne_mask) {
@@ -258,7 +279,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
   double* const stage_v = reinterpret_cast<double*>(rcp_tab + kRcpTable) + kWarpsPerCta * 128 + warp * 128 + lane;
   for (int i = threadIdx.x; i < kRcpTable; i += blockDim.x) rcp_tab[i] = (i > 0) ? 1.0 / (double)i : 0.0;
   __syncthreads();
-  LeanRing acc{rts, rval, rcp_tab, rts};
+  LeanRing acc;
+  acc.ts = rts;
+  acc.val = rval;
+  acc.rcp_tab = rcp_tab;
+  acc.init_addresses();
   const uint32_t total_warps = gridDim.x * kWarpsPerCta;
   const int32_t T = (int32_t)a.T;
   const long long tb_off = a.tb - a.offset;  // rel = ts + offset - tb
