@@ -89,9 +89,15 @@ struct LeanTraits {
 
 // 8-byte asynchronous global -> shared copy (LDGSTS): the next block's rows land in a per-warp staging area
 // without passing through registers.
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+__device__ __forceinline__ void cp_async8(uint32_t smem_dst_sa, const void* gmem_src) {  // shared-space address
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst_sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t sa, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(x) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t sa, double x) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(sa), "d"(x) : "memory"); }
+__device__ __forceinline__ long long lds_s64(uint32_t sa) {
+  long long x;
+  asm volatile("ld.shared.s64 %0, [%1];" : "=l"(x) : "r"(sa) : "memory");
+  return x;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -275,8 +281,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
   double* rval = reinterpret_cast<double*>(smem_raw) + warp * RING;
   uint32_t* rts = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kWarpsPerCta * RING * 8) + warp * (2 * RING);
   double* rcp_tab = reinterpret_cast<double*>(smem_raw + (size_t)kWarpsPerCta * RING * 16);
-  long long* const stage_t = reinterpret_cast<long long*>(rcp_tab + kRcpTable) + warp * 128 + lane;
-  double* const stage_v = reinterpret_cast<double*>(rcp_tab + kRcpTable) + kWarpsPerCta * 128 + warp * 128 + lane;
+  // staging slots of this lane (shared-space byte addresses): [2 halves][64] per warp and column, 8 B elements
+  const uint32_t stage_t = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable) + (uint32_t)(warp * 128 + lane) * 8u;
+  const uint32_t stage_v = stage_t + (uint32_t)kWarpsPerCta * 128u * 8u;
   for (int i = threadIdx.x; i < kRcpTable; i += blockDim.x) rcp_tab[i] = (i > 0) ? 1.0 / (double)i : 0.0;
   __syncthreads();
   LeanRing acc;
@@ -313,37 +320,37 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
       const double* p_v = val_s + lane;
       cp_async_wait<0>();  // a series that left the tier early may still have a block in flight into the staging area
       if ((uint32_t)lane < n) { cp_async8(stage_t, p_t); cp_async8(stage_v, p_v); }
-      if ((uint32_t)lane + 32u < n) { cp_async8(stage_t + 32, p_t + 32); cp_async8(stage_v + 32, p_v + 32); }
+      if ((uint32_t)lane + 32u < n) { cp_async8(stage_t + 256u, p_t + 32); cp_async8(stage_v + 256u, p_v + 32); }
       cp_async_commit();
-      uint32_t half = 0;  // staging half (in elements) of the block being consumed
+      uint32_t half = 0;  // staging half (byte offset 0 or 512) of the block being consumed
       while (st.j_cnt < n) {
         const uint32_t j0 = st.j_cnt;  // multiple of 64
         const uint32_t left = n - j0;
         const bool in0 = (uint32_t)lane < left, in1 = (uint32_t)lane + 32u < left;
         {
-          const uint32_t other = half ^ 64u;
+          const uint32_t other = half ^ 512u;
           if ((uint32_t)lane + 64u < left) { cp_async8(stage_t + other, p_t + 64); cp_async8(stage_v + other, p_v + 64); }
-          if ((uint32_t)lane + 96u < left) { cp_async8(stage_t + other + 32, p_t + 96); cp_async8(stage_v + other + 32, p_v + 96); }
+          if ((uint32_t)lane + 96u < left) { cp_async8(stage_t + other + 256u, p_t + 96); cp_async8(stage_v + other + 256u, p_v + 96); }
           cp_async_commit();
           p_t += 64;
           p_v += 64;
         }
         cp_async_wait<1>();  // everything but the newest group: the block to consume has landed
-        const long long c_t0 = stage_t[half], c_t1 = stage_t[half + 32];
-        const double c_v0 = stage_v[half], c_v1 = stage_v[half + 32];
-        half ^= 64u;
+        const long long c_t0 = lds_s64(stage_t + half), c_t1 = lds_s64(stage_t + half + 256u);
+        const double c_v0 = LeanRing::lds64(stage_v + half), c_v1 = LeanRing::lds64(stage_v + half + 256u);
+        half ^= 512u;
         // SeriesNormalize (offset bias) + 32-bit time domain, append to the ring: the block occupies slots
         // (j0 mod RING) + [0, 64), which never wrap, and their mirrors RING further
         const uint32_t slot = (j0 & (uint32_t)(RING - 1)) + (uint32_t)lane;
-        uint32_t* const pt = rts + slot;
-        double* const pv = rval + slot;
+        const uint32_t pt = acc.ts_sa + slot * 4u;  // shared-space addresses of the lane's first row
+        const uint32_t pv = acc.val_sa + slot * 8u;
         {
           const long long d = c_t0 - tb_off;
           const int32_t dh = (int32_t)(d >> 32);
           const uint32_t dl = (uint32_t)d;
           const uint32_t in = dl < a.rel_max ? dl : a.rel_max;
           const uint32_t r = dh == 0 ? in : (dh < 0 ? 0u : a.rel_max);
-          if (in0) { pt[0] = r; pt[RING] = r; pv[0] = c_v0; }
+          if (in0) { sts32(pt, r); sts32(pt + RING * 4u, r); sts64(pv, c_v0); }
         }
         {
           const long long d = c_t1 - tb_off;
@@ -351,14 +358,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
           const uint32_t dl = (uint32_t)d;
           const uint32_t in = dl < a.rel_max ? dl : a.rel_max;
           const uint32_t r = dh == 0 ? in : (dh < 0 ? 0u : a.rel_max);
-          if (in1) { pt[32] = r; pt[32 + RING] = r; pv[32] = c_v1; }
+          if (in1) { sts32(pt + 128u, r); sts32(pt + 128u + RING * 4u, r); sts64(pv + 256u, c_v1); }
         }
         __syncwarp();
         bool bad = (a.filter_nan != 0) & ((in0 & isnan(c_v0)) | (in1 & isnan(c_v1)));
         if constexpr (TR::kCounter) {
           // slot -1 of a series holds -inf, so its first sample never counts as a reset
-          const double p0 = rval[(slot - 1u) & (uint32_t)(RING - 1)];
-          const double p1 = pv[31];
+          const double p0 = LeanRing::lds64(acc.val_sa + (((slot - 1u) & (uint32_t)(RING - 1)) << 3));
+          const double p1 = LeanRing::lds64(pv + 248u);
           bad = bad | (in0 & (c_v0 < p0)) | (in1 & (c_v1 < p1));
         }
         if (__any_sync(0xffffffffu, bad)) { defer = 4; break; }
