@@ -1,6 +1,8 @@
 // b2p_kernels.cuh — CUDA kernels (sm_100a) of the PromQL range-query path.
 //
 //  K0 series_offsets_kernel   SeriesDivide: series boundaries from the sorted u32 id column
+//  K2L range_lean_kernel<FN>  (b2p_kernel_lean.cuh) first tier of the same fused stage: regular series only,
+//                             everything else is handed to K2 through RangeArgs::w_list
 //  K2 range_fast_kernel<FN>   SeriesNormalize + RangeManipulate + prom_* UDF + IS NOT NULL, fused:
 //                             one warp per series, samples streamed with 128-bit coalesced loads
 //                             into a per-warp shared-memory ring, lanes own consecutive eval steps
