@@ -298,8 +298,33 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
   const uint32_t te_lane0 = (uint32_t)a.range + (uint32_t)lane * (uint32_t)a.interval;
   const uint32_t te31_minus_tlo0 = (uint32_t)a.range + 31u * (uint32_t)a.interval;  // te of step k+31 minus tlo of step k
 
-  for (uint32_t s = blockIdx.x * kWarpsPerCta + warp; s < a.n_series; s += total_warps) {
-    const uint64_t row0 = a.offsets[s], row1 = a.offsets[s + 1];
+  // Block 0 of a series is put in flight (into staging half 0) before the series starts: for the first series
+  // right here, for every later one while its predecessor still evaluates its last groups; the offsets of the
+  // next series are loaded at the start of the current one.
+  auto issue_block0 = [&](uint64_t r0, uint64_t r1) {
+    const uint64_t rows = r1 - r0;
+    const uint32_t cnt = rows > 0xfffffff0ull ? 0u : (uint32_t)rows;  // oversize series are not evaluated here
+    const long long* pt0 = reinterpret_cast<const long long*>(a.ts + r0) + lane;
+    const double* pv0 = a.val + r0 + lane;
+    if ((uint32_t)lane < cnt) { cp_async8(stage_t, pt0); cp_async8(stage_v, pv0); }
+    if ((uint32_t)lane + 32u < cnt) { cp_async8(stage_t + 256u, pt0 + 32); cp_async8(stage_v + 256u, pv0 + 32); }
+    cp_async_commit();
+  };
+  uint32_t s = blockIdx.x * kWarpsPerCta + warp;
+  uint64_t row0 = 0, row1 = 0;
+  if (s < a.n_series) {
+    row0 = a.offsets[s];
+    row1 = a.offsets[s + 1];
+    issue_block0(row0, row1);
+  }
+  for (; s < a.n_series; s += total_warps) {
+    const uint32_t s_next = s + total_warps;
+    uint64_t nrow0 = 0, nrow1 = 0;
+    if (s_next < a.n_series) {
+      nrow0 = a.offsets[s_next];
+      nrow1 = a.offsets[s_next + 1];
+    }
+    bool next_issued = false;
     const uint32_t n = (uint32_t)(row1 - row0);
     int defer = ((n == 0u) || (row1 - row0 > 0xfffffff0ull)) ? 3 : 0;  // reason code, 0 = stays on this tier
     if (!defer) {
@@ -318,10 +343,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
       // in flight into the other half of the staging area (cp.async, one commit group per block)
       const long long* p_t = reinterpret_cast<const long long*>(ts_s) + lane;
       const double* p_v = val_s + lane;
-      cp_async_wait<0>();  // a series that left the tier early may still have a block in flight into the staging area
-      if ((uint32_t)lane < n) { cp_async8(stage_t, p_t); cp_async8(stage_v, p_v); }
-      if ((uint32_t)lane + 32u < n) { cp_async8(stage_t + 256u, p_t + 32); cp_async8(stage_v + 256u, p_v + 32); }
-      cp_async_commit();
       uint32_t half = 0;  // staging half (byte offset 0 or 512) of the block being consumed
       while (st.j_cnt < n) {
         const uint32_t j0 = st.j_cnt;  // multiple of 64
@@ -409,6 +430,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
       }
       if (!defer) {
         // ---- end of stream: sentinel, end trim (range_manipulate.rs:722-728), remaining groups -------
+        cp_async_wait<0>();  // (an early finish leaves a block in flight) the staging area is free from here on
+        issue_block0(nrow0, nrow1);
+        next_issued = true;
         if (lane == 0) acc.put(st.j_cnt, 0xffffffffu, 0.0);
         __syncwarp();
         int32_t kl = T - 1;
@@ -441,8 +465,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
       const uint32_t i = atomicAdd(&a.status->w_count, 1u);
       a.w_list[i] = s;
     }
+    if (!next_issued) {  // the series left the tier before its end of stream
+      cp_async_wait<0>();
+      issue_block0(nrow0, nrow1);
+    }
+    row0 = nrow0;
+    row1 = nrow1;
     __syncwarp();
   }
+  cp_async_wait<0>();
 }
 
 }  // namespace b2p

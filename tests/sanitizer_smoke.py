@@ -1,5 +1,6 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck): every kernel once, on irregular
-series, both ring variants, the slow path and the opt-in thread tier.  Not collected by pytest (no test_ prefix);
+series, both ring variants, the slow path, the lean first tier on regular series (pair groups, early finish,
+hand-off) and the opt-in thread tier.  Not collected by pytest (no test_ prefix);
 run on a GPU box:  compute-sanitizer --tool memcheck python tests/sanitizer_smoke.py"""
 import os
 import sys
@@ -31,6 +32,21 @@ def main():
         B = 4
         ctx.histogram_quantile(0.9, np.array([0.1, 1.0, 5.0, np.inf]), out[: (S // B) * B], valid[: (S // B) * B])
         ctx.close()
+    # regular series of the BASELINE shape: the lean tier's steady state (pair groups), its early finish (query ends
+    # before the data), history before the query, and the hand-off of series with resets / NaN samples
+    from oracle import oracle as orc
+    S, N, T0 = 64, 1000, 1_700_000_000_000
+    ctx = Context(0)
+    for resets in (0, 1):
+        ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, 1000, resets, 0x5EED)
+        val = val.copy()
+        val.reshape(S, N)[::8, 700] = np.nan
+        for fn in ("rate", "delta", "avg_over_time", "last_over_time"):
+            for start, end, interval, rng in ((T0, T0 + 999 * 15_000, 15_000, 300_000),
+                                              (T0 + 3_000_000, T0 + 6_000_000, 5_000, 60_000),
+                                              (T0 - 600_000, T0 + 999 * 15_000 + 900_000, 45_000, 300_000)):
+                ctx.range_eval_n(make_params(fn, start, end, interval, rng), ts, val, sid, None, S)
+    ctx.close()
     print("sanitizer smoke done")
 
 
