@@ -317,8 +317,13 @@ def run_ours(args):
     alg_k2 = 16.0 * n_rows + 8.0 * S * T + 4.0 * S * Tw + 8.0 * (S + 1)   # bytes per launch of the dominant kernel
     achieved = alg_k2 / (k2 * 1e-3) / 1e9
     lean_on = os.environ.get("B2P_DISABLE_LEAN_TIER", "0") != "1" and os.environ.get("B2P_ENABLE_THREAD_TIER", "0") != "1"
-    kernel_name = ("range_lean_kernel<rate> (+ range_fast_kernel<rate> over the series it hands off)" if lean_on
-                   else "range_fast_kernel<rate>")
+    if lean_on and warp_tier_series * 2 > S:
+        # the first tier declined most series during the warm-up (e.g. --resets 1) and backed off: K2 did the work
+        lean_on = False
+        kernel_name = "range_fast_kernel<rate> (the lean first tier handed off most series and backed off)"
+    else:
+        kernel_name = ("range_lean_kernel<rate> (+ range_fast_kernel<rate> over the series it hands off)" if lean_on
+                       else "range_fast_kernel<rate>")
     step_ms = elapsed_ms / args.steps
     read_frac = 20.0 * n_rows / (step_ms * 1e-3) / 1e9 / peak
     line = {

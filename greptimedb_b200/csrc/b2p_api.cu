@@ -90,6 +90,12 @@ struct b2p_ctx {
   bool thread_tier = false;
   // K2L, the lean warp-per-series tier in front of K2 (default on; B2P_DISABLE_LEAN_TIER=1 turns it off)
   bool lean_tier = true;
+  // adaptive tiering: when K2L handed more than half of the series of a call to K2 (e.g. every counter has resets),
+  // the next calls skip it for a while; the verdict is taken wherever the status block is read back
+  bool lean_adaptive = true;    // B2P_LEAN_ADAPTIVE=0 switches the back-off off (tests that pin the tier)
+  int lean_backoff = 0;         // range calls that still skip K2L
+  bool last_used_lean = false;  // the pending / last range call started with K2L
+  uint32_t last_range_series = 0;
   int lean_blocks_per_sm[B2P_FN__COUNT] = {};
   size_t arena_rows = 0;
   cudaEvent_t ev[4][2] = {};
@@ -385,6 +391,7 @@ b2p_ctx* b2p_create(int device) {
   }
   if (const char* e = getenv("B2P_ENABLE_THREAD_TIER")) c->thread_tier = (e[0] == '1');
   if (const char* e = getenv("B2P_DISABLE_LEAN_TIER")) c->lean_tier = !(e[0] == '1');
+  if (const char* e = getenv("B2P_LEAN_ADAPTIVE")) c->lean_adaptive = !(e[0] == '0');
   return c;
 }
 
@@ -451,6 +458,8 @@ int b2p_sync(b2p_ctx* c) {
     const Status st = *c->h_status;
     c->last_slow = st.slow_count;
     c->last_w = st.w_count;
+    if (c->lean_adaptive && c->pending_range && c->last_used_lean && (uint64_t)st.w_count * 2 > c->last_range_series)
+      c->lean_backoff = 32;
     if (st.k0_errors & 1u) return fail(B2P_E_UNSORTED, "series-id column is not non-decreasing");
     if (st.k0_errors & 2u) return fail(B2P_E_UNSORTED, "series id >= n_series");
     if (!st.arena_overflow) {
@@ -559,9 +568,15 @@ int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts,
     if (rc) return rc;
     a.use_w_list = 1;
   } else if (lean_ok(c, p->fn_id, a)) {
-    if ((rc = dispatch_lean(c, p->fn_id, a))) return rc;
-    a.use_w_list = 1;
+    if (c->lean_backoff > 0) {
+      c->lean_backoff--;
+    } else {
+      if ((rc = dispatch_lean(c, p->fn_id, a))) return rc;
+      a.use_w_list = 1;
+    }
   }
+  c->last_used_lean = a.use_w_list != 0 && !tier1;
+  c->last_range_series = n_series;
   rc = dispatch_fast(c, p->fn_id, a);
   stage_end(c, 1);
   if (rc) return rc;
@@ -959,6 +974,7 @@ int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, con
   }
   c->last_slow = slow_total;
   c->last_w = w_total;
+  if (c->lean_adaptive && c->last_used_lean && (uint64_t)w_total * 2 > n_series) c->lean_backoff = 32;
   return B2P_OK;
 }
 

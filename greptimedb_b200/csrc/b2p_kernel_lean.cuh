@@ -433,6 +433,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
         cp_async_wait<0>();  // (an early finish leaves a block in flight) the staging area is free from here on
         issue_block0(nrow0, nrow1);
         next_issued = true;
+        __syncwarp();  // lanes past the end of the last block have read (and ignored) the slot the sentinel takes
         if (lane == 0) acc.put(st.j_cnt, 0xffffffffu, 0.0);
         __syncwarp();
         int32_t kl = T - 1;

@@ -33,8 +33,15 @@ BIT_EXACT = {"resets", "changes", "count_over_time", "present_over_time", "absen
 
 @pytest.fixture(scope="module")
 def ctx():
+    """The default context, with the adaptive back-off of the lean tier pinned off so that every test below runs the
+    tier it means to run (a reset-heavy call would otherwise make the next 32 calls skip K2L)."""
+    import os
     from greptimedb_b200 import Context
-    c = Context(0)
+    os.environ["B2P_LEAN_ADAPTIVE"] = "0"
+    try:
+        c = Context(0)
+    finally:
+        del os.environ["B2P_LEAN_ADAPTIVE"]
     yield c
     c.close()
 
@@ -420,6 +427,28 @@ def test_lean_tier_keeps_regular_series_and_hands_off_the_rest(ctx, ctx_no_lean)
     op = orc.make_params("rate", T0, T0 + 999 * 15_000, 15_000, 300_000)
     e_out, e_valid = orc.range_query(op, ts, val, sid, offsets, threads=4)
     assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size), "lean tier NaN hand-off")
+
+
+def test_lean_tier_backs_off_after_a_call_it_mostly_declined(ctx_no_lean):
+    """Adaptive tiering (default on): a call in which K2L hands more than half of the series to K2 makes the following
+    calls skip K2L; results are the same either way."""
+    from greptimedb_b200 import Context, make_params
+    S, N, T0 = 256, 1000, 1_700_000_000_000
+    p = make_params("rate", T0, T0 + 999 * 15_000, 15_000, 300_000)
+    c = Context(0)
+    try:
+        ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, 1000, 1, 0x5EED)   # every series has counter resets
+        out1, valid1, _ = c.range_eval_n(p, ts, val, sid, None, S)
+        assert c.last_warp_tier_series() == S                                # K2L ran and declined all of them
+        out2, valid2, _ = c.range_eval_n(p, ts, val, sid, None, S)
+        assert c.last_warp_tier_series() == 0                                # skipped: K2 took the whole batch
+        ref, rvalid, ets = ctx_no_lean.range_eval_n(p, ts, val, sid, None, S)
+        for o, v in ((out1, valid1), (out2, valid2)):
+            assert (v == rvalid).all()
+            vb = orc.valid_to_bool(v, ets.size)
+            assert (o.view(np.uint64)[vb] == ref.view(np.uint64)[vb]).all()
+    finally:
+        c.close()
 
 
 def test_thread_tier_hands_off_what_it_cannot_do(ctx_thread_tier):
