@@ -712,3 +712,74 @@ def test_fuzz_random_queries_match_oracle(ctx, ctx_thread_tier, ctx_no_lean, see
                 assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size),
                              f"fuzz seed={seed} {fn} start={start} end={end} int={interval} rng={rng_ms} off={offset}",
                              bit_exact=fn in BIT_EXACT)
+
+
+def test_full_size_chunk_properties_and_tier_equivalence(ctx, ctx_no_lean):
+    """BASELINE config 2 at the full per-GPU chunk size (1.25 M series x 1000 samples, device-resident, through the
+    _dev C ABI): size-independent properties instead of an oracle pass over 1.25e9 samples.
+
+      * tier equivalence: K2L + K2 and K2 alone write bit-identical values and validity words;
+      * linearity: increase(x[5m]) == rate(x[5m]) * 300 to the last bits (one extra rounding: <= 2 ulp);
+      * validity: every step of every series whose window holds >= 2 samples is valid (a closed-form count for the
+        synthetic shape), and the same series re-evaluated alone (a 4096-series slice) gives the same bits — the
+        result of a series cannot depend on what else is in the batch;
+      * a sample of series against the oracle."""
+    import torch
+    from greptimedb_b200 import make_params
+    S, N, T0 = 1_250_000, 1000, 1_700_000_000_000
+    T, Tw = 1000, 32
+    dev = torch.device("cuda:0")
+    ts = torch.empty(S * N, dtype=torch.int64, device=dev)
+    val = torch.empty(S * N, dtype=torch.float64, device=dev)
+    sid = torch.empty(S * N, dtype=torch.int32, device=dev)
+    off = torch.empty(S + 1, dtype=torch.int64, device=dev)
+    outs = {}
+    for name, c in (("lean", ctx), ("k2", ctx_no_lean)):
+        c.synth_fill_dev(0, S, N, T0, 15_000, 1000, 0, 0x5EED, ts, val, sid)
+        c.series_offsets_dev(sid, S * N, S, off)
+        for fn in (("rate", "increase") if name == "lean" else ("rate",)):
+            out = torch.empty(S * T, dtype=torch.float64, device=dev)
+            valid = torch.empty(S * Tw, dtype=torch.int32, device=dev)
+            c.range_eval_dev(make_params(fn, T0, T0 + 999 * 15_000, 15_000, 300_000), ts, val, off, S * N, S, out, valid)
+            c.sync()
+            outs[(name, fn)] = (out, valid)
+        if name == "lean":
+            assert c.last_warp_tier_series() <= S // 64
+    r_lean, v_lean = outs[("lean", "rate")]
+    r_k2, v_k2 = outs[("k2", "rate")]
+    assert torch.equal(v_lean, v_k2)
+    assert torch.equal(r_lean.view(torch.int64), r_k2.view(torch.int64))
+    # validity: steps 1 .. 999 have >= 2 samples in (t - 5m, t] unless a zero-jitter sample sits on an edge; step 0 never
+    bits = v_lean.view(S, Tw)
+    popc = sum(((bits >> b) & 1).sum(dtype=torch.int64) for b in range(32))
+    n_valid = int(popc.item())
+    assert S * 997 <= n_valid <= S * 999, n_valid
+    # linearity of increase against rate
+    inc, v_inc = outs[("lean", "increase")]
+    assert torch.equal(v_inc, v_lean)
+    vb = ((bits.unsqueeze(-1) >> torch.arange(32, device=dev, dtype=torch.int32)) & 1).bool().reshape(S, Tw * 32)[:, :T]
+    mask = vb.reshape(-1)
+    rel = ((inc[mask] - r_lean[mask] * 300.0).abs() / inc[mask].abs().clamp_min(1e-300)).max().item()
+    assert rel <= 1e-15, rel
+    # a slice evaluated alone gives the same bits
+    s0, ns = 777_216, 4096
+    off2 = (off[s0:s0 + ns + 1] - off[s0]).contiguous()
+    torch.cuda.synchronize()  # off2 was produced on torch's stream, the context runs on its own
+    out2 = torch.empty(ns * T, dtype=torch.float64, device=dev)
+    valid2 = torch.empty(ns * Tw, dtype=torch.int32, device=dev)
+    r0 = s0 * N
+    ctx.range_eval_dev(make_params("rate", T0, T0 + 999 * 15_000, 15_000, 300_000), ts[r0:r0 + ns * N], val[r0:r0 + ns * N],
+                       off2, ns * N, ns, out2, valid2)
+    ctx.sync()
+    assert torch.equal(valid2, v_lean[s0 * Tw:(s0 + ns) * Tw])
+    assert torch.equal(out2.view(torch.int64), r_lean[s0 * T:(s0 + ns) * T].view(torch.int64))
+    # a sample of series against the oracle
+    pick = np.array([0, 1, 4095, 65_537, 777_216, 1_249_999])
+    h_ts = np.concatenate([ts[s * N:(s + 1) * N].cpu().numpy() for s in pick])
+    h_val = np.concatenate([val[s * N:(s + 1) * N].cpu().numpy() for s in pick])
+    offsets = np.arange(pick.size + 1, dtype=np.uint64) * N
+    op = orc.make_params("rate", T0, T0 + 999 * 15_000, 15_000, 300_000)
+    e_out, e_valid = orc.range_query(op, h_ts, h_val, None, offsets)
+    got = np.stack([r_lean[s * T:(s + 1) * T].cpu().numpy() for s in pick])
+    gv = np.stack([v_lean[s * Tw:(s + 1) * Tw].cpu().numpy().view(np.uint32) for s in pick])
+    assert_close(got, e_out, orc.valid_to_bool(gv, T), orc.valid_to_bool(e_valid, T), "full-size chunk sample vs oracle")
