@@ -93,7 +93,8 @@ struct b2p_ctx {
   // adaptive tiering: when K2L handed more than half of the series of a call to K2 (e.g. every counter has resets),
   // the next calls skip it for a while; the verdict is taken wherever the status block is read back
   bool lean_adaptive = true;    // B2P_LEAN_ADAPTIVE=0 switches the back-off off (tests that pin the tier)
-  int lean_backoff = 0;         // range calls that still skip K2L
+  int lean_backoff[B2P_FN__COUNT] = {};  // per range function: calls that still skip K2L
+  int last_range_fn = 0;
   bool last_used_lean = false;  // the pending / last range call started with K2L
   uint32_t last_range_series = 0;
   int lean_blocks_per_sm[B2P_FN__COUNT] = {};
@@ -459,7 +460,7 @@ int b2p_sync(b2p_ctx* c) {
     c->last_slow = st.slow_count;
     c->last_w = st.w_count;
     if (c->lean_adaptive && c->pending_range && c->last_used_lean && (uint64_t)st.w_count * 2 > c->last_range_series)
-      c->lean_backoff = 32;
+      c->lean_backoff[c->last_range_fn] = 32;
     if (st.k0_errors & 1u) return fail(B2P_E_UNSORTED, "series-id column is not non-decreasing");
     if (st.k0_errors & 2u) return fail(B2P_E_UNSORTED, "series id >= n_series");
     if (!st.arena_overflow) {
@@ -568,8 +569,8 @@ int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts,
     if (rc) return rc;
     a.use_w_list = 1;
   } else if (lean_ok(c, p->fn_id, a)) {
-    if (c->lean_backoff > 0) {
-      c->lean_backoff--;
+    if (c->lean_backoff[p->fn_id] > 0) {
+      c->lean_backoff[p->fn_id]--;
     } else {
       if ((rc = dispatch_lean(c, p->fn_id, a))) return rc;
       a.use_w_list = 1;
@@ -577,6 +578,7 @@ int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts,
   }
   c->last_used_lean = a.use_w_list != 0 && !tier1;
   c->last_range_series = n_series;
+  c->last_range_fn = p->fn_id;
   rc = dispatch_fast(c, p->fn_id, a);
   stage_end(c, 1);
   if (rc) return rc;
@@ -974,7 +976,7 @@ int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, con
   }
   c->last_slow = slow_total;
   c->last_w = w_total;
-  if (c->lean_adaptive && c->last_used_lean && (uint64_t)w_total * 2 > n_series) c->lean_backoff = 32;
+  if (c->lean_adaptive && c->last_used_lean && (uint64_t)w_total * 2 > n_series) c->lean_backoff[p->fn_id] = 32;
   return B2P_OK;
 }
 

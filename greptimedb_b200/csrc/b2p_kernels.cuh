@@ -512,7 +512,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_
   uint32_t* rfl = reinterpret_cast<uint32_t*>(rcp_tab + kRcpTable) + warp * FW;
   for (int i = threadIdx.x; i < kRcpTable; i += blockDim.x) rcp_tab[i] = (i > 0) ? 1.0 / (double)i : 0.0;
   __syncthreads();
-  RingAcc<RING, TS32> acc{rts, rval, rfl, rcp_tab, rts, rval, false};
+  RingAcc<RING, TS32> acc;
+  acc.init(rts, rval, rfl, rcp_tab);
   const uint32_t lt = (1u << lane) - 1u;
   const uint32_t total_warps = gridDim.x * kWarpsPerCta;
   const int32_t T = (int32_t)a.T;
