@@ -248,6 +248,7 @@ def run_ours(args):
         step()
     ev1.record()
     ctx.sync()
+    warp_tier_series = ctx.last_warp_tier_series()   # series the first tier handed to K2 in the last timed step
     barrier()
     wall1 = time.time()
     elapsed_ms = ev0.elapsed_time(ev1)
@@ -318,9 +319,12 @@ def run_ours(args):
     achieved = alg_k2 / (k2 * 1e-3) / 1e9
     lean_on = os.environ.get("B2P_DISABLE_LEAN_TIER", "0") != "1" and os.environ.get("B2P_ENABLE_THREAD_TIER", "0") != "1"
     if lean_on and warp_tier_series * 2 > S:
-        # the first tier declined most series during the warm-up (e.g. --resets 1) and backed off: K2 did the work
+        # the first tier still declined most series in the timed steps: K2 did the work
         lean_on = False
-        kernel_name = "range_fast_kernel<rate> (the lean first tier handed off most series and backed off)"
+        kernel_name = "range_fast_kernel<rate> (the lean first tier handed off most series)"
+    elif lean_on and args.resets:
+        kernel_name = ("range_lean_kernel<rate, bit words> (adaptive: the plain variant handed off every series during the "
+                       "warm-up) + range_fast_kernel<rate> over the series it hands off")
     else:
         kernel_name = ("range_lean_kernel<rate> (+ range_fast_kernel<rate> over the series it hands off)" if lean_on
                        else "range_fast_kernel<rate>")

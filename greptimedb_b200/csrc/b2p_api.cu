@@ -92,12 +92,17 @@ struct b2p_ctx {
   bool lean_tier = true;
   // adaptive tiering: when K2L handed more than half of the series of a call to K2 (e.g. every counter has resets),
   // the next calls skip it for a while; the verdict is taken wherever the status block is read back
+  bool lean_force_flags = false;  // B2P_LEAN_FORCE_FLAGS=1: rate / increase always take the bit-word variant (tests)
   bool lean_adaptive = true;    // B2P_LEAN_ADAPTIVE=0 switches the back-off off (tests that pin the tier)
-  int lean_backoff[B2P_FN__COUNT] = {};  // per range function: calls that still skip K2L
+  // per range function: 0 = plain K2L; 1 = K2L with reset bit words (rate / increase after a call that handed most
+  // series on); 2 = skip K2L.  `lean_backoff` counts the calls a non-zero mode still lasts.
+  int lean_mode[B2P_FN__COUNT] = {};
+  int lean_backoff[B2P_FN__COUNT] = {};
+  int last_lean_mode = 0;
   int last_range_fn = 0;
   bool last_used_lean = false;  // the pending / last range call started with K2L
   uint32_t last_range_series = 0;
-  int lean_blocks_per_sm[B2P_FN__COUNT] = {};
+  int lean_blocks_per_sm[B2P_FN__COUNT][2] = {};
   size_t arena_rows = 0;
   cudaEvent_t ev[4][2] = {};
   bool ev_used[4] = {false, false, false, false};
@@ -175,6 +180,15 @@ bool fits_ts32(const RangeArgs& a) {
 template <int FN>
 constexpr bool lean_supports() { return LeanTraits<FN>::kSupported; }
 
+// Adaptive tiering verdict of a finished range call that started with K2L: more than half of the series handed on ->
+// the next 32 calls of this function use the next mode (plain -> bit words for rate / increase -> skip).
+void lean_verdict(b2p_ctx* c, int fn, uint64_t handed, uint64_t n_series) {
+  if (!c->lean_adaptive || handed * 2 <= n_series) return;
+  const bool counter = (fn == B2P_FN_RATE || fn == B2P_FN_INCREASE);
+  c->lean_mode[fn] = (c->last_lean_mode == 0 && counter) ? 1 : 2;
+  c->lean_backoff[fn] = 32;
+}
+
 bool lean_fn_supported(int fn) {
   switch (fn) {
 #define X(N) case N: return lean_supports<N>();
@@ -202,11 +216,12 @@ int launch_fast(b2p_ctx* c, const RangeArgs& a) {
 // ends of the 31 steps past the grid still below the 0xFFFFFFFF end sentinel.
 bool lean_ok(const b2p_ctx* c, int fn, const RangeArgs& a);
 
-template <int FN>
+template <int FN, bool FLAGS>
 int launch_lean(b2p_ctx* c, const RangeArgs& a) {
-  constexpr size_t smem = (size_t)kWarpsPerCta * kLeanRing * 16 + kRcpTable * 8 + (size_t)kWarpsPerCta * 2 * 64 * 16;
-  auto kern = range_lean_kernel<FN>;
-  int& cached = c->lean_blocks_per_sm[FN];
+  constexpr size_t smem = (size_t)kWarpsPerCta * kLeanRing * 16 + kRcpTable * 8 + (size_t)kWarpsPerCta * 2 * 64 * 16 +
+                          (size_t)kWarpsPerCta * (kLeanRing / 32) * 4;
+  auto kern = range_lean_kernel<FN, FLAGS>;
+  int& cached = c->lean_blocks_per_sm[FN][FLAGS ? 1 : 0];
   if (cached == 0) {
     int nb = 0;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -223,17 +238,24 @@ int launch_lean(b2p_ctx* c, const RangeArgs& a) {
   return B2P_OK;
 }
 
+// `with_flags`: the variant whose ring carries the reset / change bit words (always for resets() / changes(); for
+// rate / increase when the adaptive policy picked it; never for the other functions).
 template <int FN>
-int launch_lean_if_supported(b2p_ctx* c, const RangeArgs& a) {
-  if constexpr (LeanTraits<FN>::kSupported)
-    return launch_lean<FN>(c, a);
-  else
+int launch_lean_if_supported(b2p_ctx* c, const RangeArgs& a, bool with_flags) {
+  if constexpr (!LeanTraits<FN>::kSupported) {
     return fail(B2P_E_INVALID, "fn_id %d has no lean tier", FN);
+  } else if constexpr (LeanTraits<FN>::kNeedsFlags) {
+    return launch_lean<FN, true>(c, a);
+  } else if constexpr (LeanTraits<FN>::kHasFlagsVariant) {
+    return with_flags ? launch_lean<FN, true>(c, a) : launch_lean<FN, false>(c, a);
+  } else {
+    return launch_lean<FN, false>(c, a);
+  }
 }
 
-int dispatch_lean(b2p_ctx* c, int fn, const RangeArgs& a) {
+int dispatch_lean(b2p_ctx* c, int fn, const RangeArgs& a, bool with_flags) {
   switch (fn) {
-#define X(N) case N: return launch_lean_if_supported<N>(c, a);
+#define X(N) case N: return launch_lean_if_supported<N>(c, a, with_flags);
     X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20)
 #undef X
   }
@@ -393,6 +415,7 @@ b2p_ctx* b2p_create(int device) {
   if (const char* e = getenv("B2P_ENABLE_THREAD_TIER")) c->thread_tier = (e[0] == '1');
   if (const char* e = getenv("B2P_DISABLE_LEAN_TIER")) c->lean_tier = !(e[0] == '1');
   if (const char* e = getenv("B2P_LEAN_ADAPTIVE")) c->lean_adaptive = !(e[0] == '0');
+  if (const char* e = getenv("B2P_LEAN_FORCE_FLAGS")) c->lean_force_flags = (e[0] == '1');
   return c;
 }
 
@@ -459,8 +482,7 @@ int b2p_sync(b2p_ctx* c) {
     const Status st = *c->h_status;
     c->last_slow = st.slow_count;
     c->last_w = st.w_count;
-    if (c->lean_adaptive && c->pending_range && c->last_used_lean && (uint64_t)st.w_count * 2 > c->last_range_series)
-      c->lean_backoff[c->last_range_fn] = 32;
+    if (c->pending_range && c->last_used_lean) lean_verdict(c, c->last_range_fn, st.w_count, c->last_range_series);
     if (st.k0_errors & 1u) return fail(B2P_E_UNSORTED, "series-id column is not non-decreasing");
     if (st.k0_errors & 2u) return fail(B2P_E_UNSORTED, "series id >= n_series");
     if (!st.arena_overflow) {
@@ -569,10 +591,14 @@ int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts,
     if (rc) return rc;
     a.use_w_list = 1;
   } else if (lean_ok(c, p->fn_id, a)) {
+    int mode = 0;
     if (c->lean_backoff[p->fn_id] > 0) {
       c->lean_backoff[p->fn_id]--;
-    } else {
-      if ((rc = dispatch_lean(c, p->fn_id, a))) return rc;
+      mode = c->lean_mode[p->fn_id];
+    }
+    c->last_lean_mode = mode;
+    if (mode != 2) {
+      if ((rc = dispatch_lean(c, p->fn_id, a, mode == 1 || c->lean_force_flags))) return rc;
       a.use_w_list = 1;
     }
   }
@@ -976,7 +1002,7 @@ int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, con
   }
   c->last_slow = slow_total;
   c->last_w = w_total;
-  if (c->lean_adaptive && c->last_used_lean && (uint64_t)w_total * 2 > n_series) c->lean_backoff[p->fn_id] = 32;
+  if (c->last_used_lean) lean_verdict(c, p->fn_id, (uint64_t)w_total, n_series);
   return B2P_OK;
 }
 

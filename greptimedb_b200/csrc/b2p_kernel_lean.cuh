@@ -36,10 +36,13 @@ constexpr int kLeanRing = 256;
 // The per-warp sample ring of this tier.  Timestamps (uint32 ms since start - range) are stored twice, slot p
 // and slot p + RING, so the edge reads around an index need no wrap handling after set_window(); values are
 // stored once and read through a mask (two reads per step), which keeps four CTAs per SM inside shared memory.
-struct LeanRing {
+template <bool FLAGS>
+struct LeanRingT {
   using time_type = uint32_t;
   static constexpr int RING = kLeanRing;
-  static constexpr bool kHasFlags = false;  // series with counter resets leave the tier; resets()/changes() never enter
+  // FLAGS: the ring also carries the reset / change bit of every sample (8 words per warp), like the second tier's.
+  // Without them a series with a counter reset leaves the tier.
+  static constexpr bool kHasFlags = FLAGS;
   static constexpr bool kHasRcp = true;
   uint32_t* ts;            // [2*RING]
   double* val;             // [RING]
@@ -47,6 +50,8 @@ struct LeanRing {
   // the same three arrays as 32-bit shared-space byte addresses: the hot reads go through ld.shared with a plain
   // register base (a generic pointer makes the compiler rebuild the shared window base around every use)
   uint32_t ts_sa, val_sa, rcp_sa;
+  uint32_t flags_sa;       // [RING/32] bit words (FLAGS only)
+  bool no_flags;           // warp-uniform hint: no set bit can lie inside any window of this group
   uint32_t lin_sa;         // ts_sa + 4 * ((j0 & (RING-1)) - j0)
   __device__ __forceinline__ void init_addresses() {
     ts_sa = (uint32_t)__cvta_generic_to_shared(ts);
@@ -75,16 +80,21 @@ struct LeanRing {
   __device__ __forceinline__ uint32_t tm(uint32_t j) const { return lds32(ts_sa + ((j & (RING - 1)) << 2)); }
   __device__ __forceinline__ double v(uint32_t j) const { return lds64(val_sa + ((j & (RING - 1)) << 3)); }
   __device__ __forceinline__ double rcp(uint32_t n) const { return lds64(rcp_sa + (n << 3)); }
-  __device__ __forceinline__ uint32_t fw(uint32_t) const { return 0u; }
+  __device__ __forceinline__ uint32_t fw(uint32_t w) const {
+    if constexpr (FLAGS) return lds32(flags_sa + ((w & (uint32_t)(RING / 32 - 1)) << 2));
+    else return 0u;
+  }
 };
 
-// Range functions this tier evaluates: everything whose value only depends on the window's samples and that is
-// null on an empty window.  resets()/changes() need the reset/change bit words of the second tier; absent_over_time,
-// quantile_over_time and holt_winters yield a value on an EMPTY window, which needs the series-level veto
-// (range_manipulate.rs:641-643) the second tier implements.
+// Range functions this tier evaluates: everything that is null on an empty window (absent_over_time,
+// quantile_over_time and holt_winters yield a value there, which needs the series-level veto of
+// range_manipulate.rs:641-643 that the second tier implements).  resets() / changes() run the FLAGS variant;
+// rate / increase run the plain one and switch to FLAGS when most series of a call had counter resets.
 template <int FN>
 struct LeanTraits {
-  static constexpr bool kSupported = !(FN == B2P_FN_RESETS || FN == B2P_FN_CHANGES || FnTraits<FN>::kSomeOnEmpty);
+  static constexpr bool kSupported = !FnTraits<FN>::kSomeOnEmpty;
+  static constexpr bool kNeedsFlags = (FN == B2P_FN_RESETS || FN == B2P_FN_CHANGES);  // only the FLAGS variant
+  static constexpr bool kHasFlagsVariant = FnTraits<FN>::kUsesFlags;                  // rate / increase too
 };
 
 // 8-byte asynchronous global -> shared copy (LDGSTS): the next block's rows land in a per-warp staging area
@@ -112,11 +122,12 @@ struct LeanState {  // warp-uniform
   // 2 = after it, 3 = like 1 but the cursor start handed to the next step is >= m: a non-empty window there
   // would hit the overshoot quirk
   uint32_t phase;
+  uint32_t last_flag;  // FLAGS variant: ordinal of the newest set reset / change bit (0 = none yet)
 };
 
 // The value of one step whose window [q, g] (both edge timestamps known) is already established.
-template <int FN>
-__device__ __forceinline__ double lean_value(const RangeArgs& a, const LeanRing& acc, int32_t g, uint32_t q,
+template <int FN, bool FLAGS>
+__device__ __forceinline__ double lean_value(const RangeArgs& a, const LeanRingT<FLAGS>& acc, int32_t g, uint32_t q,
                                              uint32_t t_lo, uint32_t t_hi, uint32_t te, bool& ok) {
   const uint32_t l = (uint32_t)(g + 1) - q;  // 0 for an empty window (q == g + 1)
   double r = 0.0;
@@ -125,8 +136,10 @@ __device__ __forceinline__ double lean_value(const RangeArgs& a, const LeanRing&
     if (ok) {
       const double first_value = acc.v(q);
       const double last_value = acc.v((uint32_t)g);
-      // counters add the reset correction, 0.0 on this tier (keeps the sign of a zero difference identical)
-      const double result_value = FnTraits<FN>::kCounter ? (last_value - first_value) + 0.0 : last_value - first_value;
+      // counters add the reset correction: from the bit words (FLAGS), else 0.0 — no series with a reset stays on
+      // the plain variant (adding 0.0 keeps the sign of a zero difference identical)
+      double result_value = last_value - first_value;
+      if constexpr (FnTraits<FN>::kCounter) result_value += FLAGS ? reset_correction(acc, q, (uint32_t)g) : 0.0;
       r = extrapolate_parts<FN, uint32_t, true>(result_value, first_value, t_lo, t_hi, l, te, (uint32_t)a.range,
                                                 acc.rcp(l - 1u), a.range_secs, a.rcp_rs);
     }
@@ -139,8 +152,8 @@ __device__ __forceinline__ double lean_value(const RangeArgs& a, const LeanRing&
 
 // One aligned group of 32 steps; lane's step is k (window end te, start tlo = te - range, both in the 32-bit
 // domain).  Returns 0, or the reason (> 0) why the series has to go to the second tier.
-template <int FN, bool TAIL>
-__device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, LeanRing& acc,
+template <int FN, bool TAIL, bool FLAGS>
+__device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, LeanRingT<FLAGS>& acc,
                                            uint32_t m, uint32_t te, int32_t k, int32_t kl, double* out_p,
                                            uint32_t* vw_p, int lane) {
   const uint32_t rng = (uint32_t)a.range;
@@ -148,6 +161,7 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Lea
   const int32_t top = (int32_t)st.j_cnt - 1;
   const uint32_t lane1 = (uint32_t)lane + 1u;
   acc.set_window((int32_t)st.base_lo - 1);
+  if constexpr (FLAGS) acc.no_flags = st.last_flag <= st.base_lo;  // no bit can lie inside a window of this group
   int32_t g = st.base_hi + (int32_t)((lane1 * st.d_hi) >> 5);
   uint32_t q = st.base_lo + ((lane1 * st.d_lo) >> 5);
   // before the end of the stream the newest sample is younger than every window end of the group, so a
@@ -214,7 +228,7 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Lea
     st.base_lo = nlo;
   }
   bool ok;
-  double r = lean_value<FN>(a, acc, g, q, t_lo, t_hi, te, ok);
+  double r = lean_value<FN, FLAGS>(a, acc, g, q, t_lo, t_hi, te, ok);
   if (TAIL && k > kl) {  // trimmed by RangeManipulate's end alignment
     ok = false;
     r = 0.0;
@@ -234,8 +248,8 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Lea
 // non-empty, at most one sample of advance per step (so no cursor start can reach m, see lean_group), and every
 // one of the 64 proportional guesses verified by one vote.  Returns false without side effects when any of that
 // does not hold; the caller then takes the groups one at a time.
-template <int FN>
-__device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, LeanRing& acc, uint32_t te,
+template <int FN, bool FLAGS>
+__device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, LeanRingT<FLAGS>& acc, uint32_t te,
                                           uint32_t step32, double* out_p, uint32_t* vw_p, int lane) {
   const int32_t top = (int32_t)st.j_cnt - 1;
   // uniform gates; the last two keep every read below the newest sample (slot top), i.e. on written slots
@@ -246,6 +260,7 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
   const uint32_t te_b = te + step32;
   const uint32_t tlo_a = te - rng, tlo_b = te_b - rng;
   acc.set_window((int32_t)st.base_lo - 1);
+  if constexpr (FLAGS) acc.no_flags = st.last_flag <= st.base_lo;  // no bit can lie inside a window of this group
   const int32_t g_a = st.base_hi + (int32_t)((lane1 * st.d_hi) >> 5), g_b = g_a + (int32_t)st.d_hi;
   const uint32_t q_a = st.base_lo + ((lane1 * st.d_lo) >> 5), q_b = q_a + st.d_lo;
   const uint32_t t_hi_a = acc.t((uint32_t)g_a), t_hi1_a = acc.t((uint32_t)(g_a + 1));
@@ -258,9 +273,9 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
   st.base_hi += 2 * (int32_t)st.d_hi;
   st.base_lo += 2u * st.d_lo;
   bool ok_a, ok_b;
-  const double r_a = lean_value<FN>(a, acc, g_a, q_a, t_lo_a, t_hi_a, te, ok_a);
+  const double r_a = lean_value<FN, FLAGS>(a, acc, g_a, q_a, t_lo_a, t_hi_a, te, ok_a);
   out_p[0] = r_a;
-  const double r_b = lean_value<FN>(a, acc, g_b, q_b, t_lo_b, t_hi_b, te_b, ok_b);
+  const double r_b = lean_value<FN, FLAGS>(a, acc, g_b, q_b, t_lo_b, t_hi_b, te_b, ok_b);
   out_p[32] = r_b;
   const uint32_t vw_a = __ballot_sync(0xffffffffu, ok_a), vw_b = __ballot_sync(0xffffffffu, ok_b);
   if (lane == 0) {
@@ -270,14 +285,16 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
   return true;
 }
 
-template <int FN>
+template <int FN, bool FLAGS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_lean_kernel(const RangeArgs a) {
+  using LeanRing = LeanRingT<FLAGS>;
   constexpr int RING = kLeanRing;
   using TR = FnTraits<FN>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // smem: [warps][RING] val f64 | [warps][2*RING] ts u32 | [kRcpTable] f64 | [warps][2][64] ts i64 |
-  //       [warps][2][64] val f64 (staging of the block being fetched and the block being consumed)
+  //       [warps][2][64] val f64 (staging of the block being fetched and the block being consumed) |
+  //       [warps][RING/32] reset / change bit words (FLAGS variant)
   double* rval = reinterpret_cast<double*>(smem_raw) + warp * RING;
   uint32_t* rts = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kWarpsPerCta * RING * 8) + warp * (2 * RING);
   double* rcp_tab = reinterpret_cast<double*>(smem_raw + (size_t)kWarpsPerCta * RING * 16);
@@ -291,6 +308,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
   acc.val = rval;
   acc.rcp_tab = rcp_tab;
   acc.init_addresses();
+  acc.flags_sa = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable + kWarpsPerCta * 256) + (uint32_t)warp * (RING / 32) * 4u;
+  acc.no_flags = true;
   const uint32_t total_warps = gridDim.x * kWarpsPerCta;
   const int32_t T = (int32_t)a.T;
   const long long tb_off = a.tb - a.offset;  // rel = ts + offset - tb
@@ -333,7 +352,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
       double* out_p = a.out + (size_t)s * (size_t)T + lane;
       uint32_t* vw_p = a.valid + (size_t)s * a.Tw;
       LeanState st;
-      st.j_cnt = 0; st.base_lo = 0; st.base_hi = -1; st.d_lo = 0; st.d_hi = 32; st.phase = 0;
+      st.j_cnt = 0; st.base_lo = 0; st.base_hi = -1; st.d_lo = 0; st.d_hi = 32; st.phase = 0; st.last_flag = 0;
       uint32_t te = te_lane0;                                      // window end of step k_next + lane
       uint32_t te31 = (uint32_t)a.range + 31u * (uint32_t)a.interval;  // ... of step k_next + 31
       __syncwarp();
@@ -383,25 +402,42 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
         }
         __syncwarp();
         bool bad = (a.filter_nan != 0) & ((in0 & isnan(c_v0)) | (in1 & isnan(c_v1)));
-        if constexpr (TR::kCounter) {
+        if constexpr (FLAGS) {
+          // reset / change bit of every new sample against its predecessor (slot -1 of a series holds -inf, so
+          // its first sample is never a reset; for changes() it is masked explicitly): the block is 64-aligned,
+          // so its two ballots are exactly two bit words
+          const double p0 = LeanRing::lds64(acc.val_sa + (((slot - 1u) & (uint32_t)(RING - 1)) << 3));
+          const double p1 = LeanRing::lds64(pv + 248u);
+          bool f0 = in0 & flag_pred<FN>(c_v0, p0);
+          const bool f1 = in1 & flag_pred<FN>(c_v1, p1);
+          if constexpr (TR::kFlagChange) f0 = f0 & ((j0 | (uint32_t)lane) != 0u);
+          const uint32_t b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+          if (lane == 0) {
+            sts32(acc.flags_sa + (((j0 >> 5) & (uint32_t)(RING / 32 - 1)) << 2), b0);
+            sts32(acc.flags_sa + ((((j0 >> 5) + 1u) & (uint32_t)(RING / 32 - 1)) << 2), b1);
+          }
+          if (b1) st.last_flag = j0 + 63u - (uint32_t)__clz(b1);
+          else if (b0) st.last_flag = j0 + 31u - (uint32_t)__clz(b0);
+        } else if constexpr (TR::kCounter) {
           // slot -1 of a series holds -inf, so its first sample never counts as a reset
           const double p0 = LeanRing::lds64(acc.val_sa + (((slot - 1u) & (uint32_t)(RING - 1)) << 3));
           const double p1 = LeanRing::lds64(pv + 248u);
           bad = bad | (in0 & (c_v0 < p0)) | (in1 & (c_v1 < p1));
         }
         if (__any_sync(0xffffffffu, bad)) { defer = 4; break; }
+        if constexpr (FLAGS) __syncwarp();  // the bit words are read by every lane below
         st.j_cnt = j0 + (left < 64u ? left : 64u);
         const uint32_t t_new = acc.tm(st.j_cnt - 1u);
         // every group whose last window end is older than the newest sample is final
         while (te31 < t_new) {
-          if (B2P_LEAN_PAIR && te31 + step32 < t_new && lean_pair<FN>(a, st, acc, te, step32, out_p, vw_p, lane)) {
+          if (B2P_LEAN_PAIR && te31 + step32 < t_new && lean_pair<FN, FLAGS>(a, st, acc, te, step32, out_p, vw_p, lane)) {
             te += 2u * step32;
             te31 += 2u * step32;
             out_p += 64;
             vw_p += 2;
             continue;
           }
-          if ((defer = lean_group<FN, false>(a, st, acc, n, te, 0, 0, out_p, vw_p, lane))) break;
+          if ((defer = lean_group<FN, false, FLAGS>(a, st, acc, n, te, 0, 0, out_p, vw_p, lane))) break;
           te += step32;
           te31 += step32;
           out_p += 32;
@@ -452,7 +488,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
           }
         }
         for (int32_t k_next = (int32_t)(out_p - (a.out + (size_t)s * (size_t)T + lane)); k_next < T; k_next += 32) {
-          if ((defer = lean_group<FN, true>(a, st, acc, n, te, k_next + lane, kl, out_p, vw_p, lane))) break;
+          if ((defer = lean_group<FN, true, FLAGS>(a, st, acc, n, te, k_next + lane, kl, out_p, vw_p, lane))) break;
           te += step32;
           out_p += 32;
           vw_p += 1;

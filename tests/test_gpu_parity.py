@@ -336,16 +336,33 @@ def ctx_no_lean():
     c.close()
 
 
+@pytest.fixture(scope="module")
+def ctx_lean_flags():
+    """A context whose lean tier always runs the bit-word variant for rate / increase (the one the adaptive policy
+    switches to after a reset-heavy call), with the adaptive policy itself pinned off."""
+    import os
+    from greptimedb_b200 import Context
+    os.environ["B2P_LEAN_FORCE_FLAGS"] = "1"
+    os.environ["B2P_LEAN_ADAPTIVE"] = "0"
+    try:
+        c = Context(0)
+    finally:
+        del os.environ["B2P_LEAN_FORCE_FLAGS"]
+        del os.environ["B2P_LEAN_ADAPTIVE"]
+    yield c
+    c.close()
+
+
 RATE_EXACT_SHAPES = ((1000, 1, 300_000), (0, 0, 300_000), (977, 1, 77_777), (1000, 0, 1_000_000))
 
 
-@pytest.mark.parametrize("lean", [True, False])
-def test_rate_warp_tier_is_bit_exact_against_the_rescan_oracle(ctx, ctx_no_lean, lean):
+@pytest.mark.parametrize("lean", [True, False, "flags"])
+def test_rate_warp_tier_is_bit_exact_against_the_rescan_oracle(ctx, ctx_no_lean, ctx_lean_flags, lean):
     """Warp-per-series kernels (lean tier + K2, or K2 alone): the two-FMA divisions (by window length, by range
     seconds) must round exactly like IEEE division, and the bitmask reset correction must add exactly what the
     reference's rescan adds."""
     from greptimedb_b200 import make_params
-    ctx = ctx if lean else ctx_no_lean
+    ctx = ctx_lean_flags if lean == "flags" else (ctx if lean else ctx_no_lean)
     S, N, T0 = 256, 1000, 1_700_000_000_000
     for jitter, resets, rng_ms in RATE_EXACT_SHAPES:
         ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, jitter, resets, 0x5EED)
@@ -689,7 +706,7 @@ def _fuzz_series(rng, n_series):
 
 
 @pytest.mark.parametrize("seed", range(12))
-def test_fuzz_random_queries_match_oracle(ctx, ctx_thread_tier, ctx_no_lean, seed):
+def test_fuzz_random_queries_match_oracle(ctx, ctx_thread_tier, ctx_no_lean, ctx_lean_flags, seed):
     """Random series zoo x random (start, end, interval, range, offset): validity bit-exact, values <= 1e-9 rel."""
     from greptimedb_b200 import make_params
     rng = np.random.default_rng(1000 + seed)
@@ -707,7 +724,7 @@ def test_fuzz_random_queries_match_oracle(ctx, ctx_thread_tier, ctx_no_lean, see
             p = make_params(fn, start, end, interval, rng_ms, offset=offset, param0=0.75)
             op = orc.make_params(fn, start, end, interval, rng_ms, offset=offset, param0=0.75)
             e_out, e_valid = orc.range_query(op, ts, val, None, offsets)
-            for c in ((ctx, ctx_thread_tier, ctx_no_lean) if fn in ("rate", "increase", "delta") else (ctx,)):
+            for c in ((ctx, ctx_thread_tier, ctx_no_lean, ctx_lean_flags) if fn in ("rate", "increase", "delta") else (ctx,)):
                 out, valid, ets = c.range_eval(p, ts, val, offsets=offsets)
                 assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size),
                              f"fuzz seed={seed} {fn} start={start} end={end} int={interval} rng={rng_ms} off={offset}",
