@@ -4,7 +4,8 @@
   python bench.py --gpus N --steps K --warmup W            # our CUDA path  (one JSON line on rank 0)
   python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU path (oracle port)
 
-A "step" is one pass of the hot path (K0 series offsets + K2 fused normalize/range/rate kernel) over
+A "step" is one pass of the hot path (K0 series offsets + the fused normalize/range/rate stage: K2L first tier,
+K2 over the series it hands off, slow kernel over what K2 hands off) over
 one HBM-resident chunk of synthetic series of the BASELINE config-2 shape: 1000 samples/series at a
 15 s scrape (+<1 s jitter), rate(x[5m]) at a 15 s step => 1000 eval steps.  Config 2's 10 M series
 (200 GB of input) exceed one GPU's HBM, so they are processed as 8 chunks of 1.25 M series; the

@@ -1,18 +1,19 @@
-// b2p_kernel_lean.cuh — K2L: the lean first tier of the fused range kernel (rate / increase / delta).
+// b2p_kernel_lean.cuh — K2L: the lean first tier of the fused range kernel (18 of the 21 range functions).
 //
-// Same contract as range_fast_kernel (SeriesNormalize -> RangeManipulate -> prom_rate/increase/delta ->
-// IS NOT NULL for every series of the batch, one warp per series, samples streamed into a per-warp
-// shared-memory ring, one eval step per lane), but it only keeps the work the common series needs and hands
-// every series that needs more to range_fast_kernel through RangeArgs::w_list (which in turn hands the
-// cursor-overshoot / long-window cases to range_slow_kernel).  A series stays on this tier while
+// Same contract as range_fast_kernel (SeriesNormalize -> RangeManipulate -> prom_* UDF -> IS NOT NULL for every
+// series of the batch, one warp per series, samples streamed into a per-warp shared-memory ring, one eval step
+// per lane), but it only keeps the work the common series needs and hands every series that needs more to
+// range_fast_kernel through RangeArgs::w_list (which in turn hands the cursor-overshoot / long-window cases to
+// range_slow_kernel).  A series stays on this tier while
 //   * no sample is dropped by SeriesNormalize (normalize.rs:417-426: NaN values with filter_nan),
-//   * no counter reset occurs (extrapolate_rate.rs:226-233 would add a correction),
+//   * no counter reset occurs (plain variant of rate / increase: extrapolate_rate.rs:226-233 would add a
+//     correction; the FLAGS variant carries the reset / change bit words and keeps such series),
 //   * every window and the 64-row block behind it fit the ring,
 //   * the windows of the evaluated steps are empty only before the first and after the last non-empty one,
 //   * calculate_range's cursor start (range_manipulate.rs:741) stays below the number of
 //     samples of the series wherever the next window is non-empty (the overshoot quirk needs the slow kernel).
 // What it does evaluate is bit-identical to the second tier: window edges are the definitional ones
-// (verified guesses, else a walk), the arithmetic is the same extrapolate_parts.
+// (verified guesses, else a walk), the arithmetic is the same extrapolate_parts / eval_window.
 //
 // Differences that make it cheap:
 //   * sentinels instead of bounds: ring slot -1 holds (ts 0, -inf) and, after the last row, slot m holds
@@ -20,7 +21,11 @@
 //   * readiness without division: a group of 32 steps is evaluated as soon as the window end of its last
 //     step is older than the newest sample (te31 < t_new), tracked incrementally;
 //   * proportional edge guesses (lane+1)*d/32 from the previous group's total advance, verified by four
-//     ring reads; when they hold, the next bases follow without shuffles;
+//     ring reads; when they hold, the next bases follow without shuffles; two groups (64 steps) per vote
+//     whenever two are ready;
+//   * rows arrive through cp.async into a per-warp staging area (no prefetch registers), the next series'
+//     offsets and first block are fetched while the current one evaluates its last groups;
+//   * the hot shared-memory reads / stores use 32-bit shared-space addresses (ld.shared / st.shared);
 //   * the end trim (range_manipulate.rs:722-728) is applied to the tail groups only — every step
 //     evaluated before the end of the stream is below the trimmed end when range >= interval (host gate).
 #pragma once
