@@ -31,40 +31,75 @@ struct GroupArgs {
   int32_t accumulate;  // 1: add into existing out_val/out_cnt (SUM/COUNT partial chaining)
 };
 
+// AGG is a compile-time constant so that the per-member fold is one or two instructions (sum / avg / count) instead
+// of a switch inside the inner loop.
+template <int AGG>
 __global__ void __launch_bounds__(256) group_aggregate_kernel(const GroupArgs a) {
   const int lane = threadIdx.x & 31;
   const uint64_t tiles = (a.T + 31) / 32;
   const uint64_t total = (uint64_t)a.n_groups * tiles;
+  const uint32_t tiles32 = (uint32_t)tiles;
+  const bool small = total < 0xffffffffull;  // 32-bit task arithmetic (always, in practice)
   for (uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total;
        w += ((uint64_t)gridDim.x * blockDim.x) >> 5) {
-    const uint32_t g = (uint32_t)(w / tiles);
-    const uint64_t tile = w - (uint64_t)g * tiles;
+    uint32_t g;
+    uint64_t tile;
+    if (small) {
+      g = (uint32_t)w / tiles32;
+      tile = (uint32_t)w - g * tiles32;
+    } else {
+      g = (uint32_t)(w / tiles);
+      tile = w - (uint64_t)g * tiles;
+    }
     const uint64_t k = tile * 32 + lane;
     const bool in = k < a.T;
     const uint32_t m0 = a.goff[g], m1 = a.goff[g + 1];
     double acc = 0.0, mean = 0.0, m2 = 0.0;
     uint32_t cnt = 0;
-    for (uint32_t mi = m0; mi < m1; ++mi) {
-      const uint32_t s = a.members[mi];
-      const uint32_t word = a.valid[(size_t)s * a.Tw + tile];
-      if (in && ((word >> lane) & 1u)) {
-        const double x = a.vals[(size_t)s * a.T + k];
-        switch (a.agg) {
-          case B2P_AGG_SUM:
-          case B2P_AGG_AVG: acc += x; break;
-          case B2P_AGG_COUNT: break;
-          case B2P_AGG_MIN: if (cnt == 0 || x < acc || (isnan(acc) && !isnan(x))) acc = x; break;
-          case B2P_AGG_MAX: if (cnt == 0 || x > acc || (isnan(acc) && !isnan(x))) acc = x; break;
-          default: {  // Welford, population variance
-            const double new_count = (double)cnt + 1.0;
-            const double delta1 = x - mean;
-            const double new_mean = delta1 / new_count + mean;
-            const double delta2 = x - new_mean;
-            m2 += delta1 * delta2;
-            mean = new_mean;
-          }
+    auto fold = [&](double x) {
+      if constexpr (AGG == B2P_AGG_SUM || AGG == B2P_AGG_AVG) {
+        acc += x;
+      } else if constexpr (AGG == B2P_AGG_COUNT) {
+      } else if constexpr (AGG == B2P_AGG_MIN) {
+        if (cnt == 0 || x < acc || (isnan(acc) && !isnan(x))) acc = x;
+      } else if constexpr (AGG == B2P_AGG_MAX) {
+        if (cnt == 0 || x > acc || (isnan(acc) && !isnan(x))) acc = x;
+      } else {  // Welford, population variance
+        const double new_count = (double)cnt + 1.0;
+        const double delta1 = x - mean;
+        const double new_mean = delta1 / new_count + mean;
+        const double delta2 = x - new_mean;
+        m2 += delta1 * delta2;
+        mean = new_mean;
+      }
+      ++cnt;
+    };
+    // Up to 32 members at a time: lane i fetches member i's series id and validity word (two dependent loads for
+    // the whole batch instead of two per member), then the 256-byte value segments are requested four members
+    // ahead of their use; the fold itself stays in member (= series) order.
+    const double* const vals_k = a.vals + k;  // lane's column inside a series' row
+    for (uint32_t mb = m0; mb < m1; mb += 32) {
+      const uint32_t nm = (m1 - mb < 32u) ? (m1 - mb) : 32u;
+      uint32_t s_l = 0, bit_l = 0;
+      if ((uint32_t)lane < nm) {
+        s_l = a.members[mb + lane];
+        bit_l = a.valid[(size_t)s_l * a.Tw + tile];
+      }
+      for (uint32_t j = 0; j < nm; j += 4) {
+        double x[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t src = (j + u < nm) ? j + u : j;  // shuffles stay warp-uniform past the batch end
+          const uint32_t s = __shfl_sync(0xffffffffu, s_l, (int)src);
+          const uint32_t word = __shfl_sync(0xffffffffu, bit_l, (int)src);
+          ok[u] = (j + u < nm) && in && ((word >> lane) & 1u);
+          x[u] = 0.0;
+          if (ok[u]) x[u] = vals_k[(size_t)s * a.T];
         }
-        ++cnt;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (ok[u]) fold(x[u]);
       }
     }
     if (!in) continue;
@@ -76,15 +111,11 @@ __global__ void __launch_bounds__(256) group_aggregate_kernel(const GroupArgs a)
     }
     double r = 0.0;
     if (cnt > 0) {
-      switch (a.agg) {
-        case B2P_AGG_SUM: r = acc; break;
-        case B2P_AGG_AVG: r = acc / (double)cnt; break;
-        case B2P_AGG_COUNT: r = (double)cnt; break;
-        case B2P_AGG_MIN:
-        case B2P_AGG_MAX: r = acc; break;
-        case B2P_AGG_STDVAR: r = m2 / (double)cnt; break;
-        default: r = sqrt(m2 / (double)cnt); break;
-      }
+      if constexpr (AGG == B2P_AGG_SUM || AGG == B2P_AGG_MIN || AGG == B2P_AGG_MAX) r = acc;
+      else if constexpr (AGG == B2P_AGG_AVG) r = acc / (double)cnt;
+      else if constexpr (AGG == B2P_AGG_COUNT) r = (double)cnt;
+      else if constexpr (AGG == B2P_AGG_STDVAR) r = m2 / (double)cnt;
+      else r = sqrt(m2 / (double)cnt);
     }
     a.out_val[o] = r;
     a.out_cnt[o] = cnt;

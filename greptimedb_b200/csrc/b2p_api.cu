@@ -659,9 +659,23 @@ int b2p_instant_select_dev(b2p_ctx* c, int64_t start, int64_t end, int64_t inter
   return B2P_OK;
 }
 
+namespace {
+int group_aggregate_impl(b2p_ctx* c, int32_t agg, const double* vals, const uint32_t* valid_words, const uint32_t* gid,
+                         uint32_t n_series, uint32_t n_groups, uint64_t T, double* out_val, uint32_t* out_cnt,
+                         int accumulate);
+}
+
 int b2p_group_aggregate_dev(b2p_ctx* c, int32_t agg, const double* vals, const uint32_t* valid_words,
                             const uint32_t* gid, uint32_t n_series, uint32_t n_groups, uint64_t T, double* out_val,
                             uint32_t* out_cnt) {
+  return group_aggregate_impl(c, agg, vals, valid_words, gid, n_series, n_groups, T, out_val, out_cnt, 0);
+}
+
+namespace {
+// accumulate = 1 (SUM / COUNT partials only): out_val / out_cnt are added to instead of overwritten
+int group_aggregate_impl(b2p_ctx* c, int32_t agg, const double* vals, const uint32_t* valid_words, const uint32_t* gid,
+                         uint32_t n_series, uint32_t n_groups, uint64_t T, double* out_val, uint32_t* out_cnt,
+                         int accumulate) {
   if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
   if (agg < 0 || agg > B2P_AGG_STDVAR) return fail(B2P_E_INVALID, "unknown aggregator %d", agg);
   if (n_groups == 0 || T == 0) return B2P_OK;
@@ -692,17 +706,26 @@ int b2p_group_aggregate_dev(b2p_ctx* c, int32_t agg, const double* vals, const u
   GroupArgs a{};
   a.agg = agg; a.vals = vals; a.valid = valid_words; a.goff = c->g_goff.as<uint32_t>();
   a.members = c->g_vals_out.as<uint32_t>(); a.n_groups = n_groups; a.T = T; a.Tw = (uint32_t)((T + 31) / 32);
-  a.out_val = out_val; a.out_cnt = out_cnt; a.accumulate = 0;
+  a.out_val = out_val; a.out_cnt = out_cnt; a.accumulate = accumulate;
   const uint64_t warps = (uint64_t)n_groups * ((T + 31) / 32);
   uint64_t blocks = (warps + 7) / 8;
   const uint64_t cap = (uint64_t)c->num_sms * 32;
   if (blocks > cap) blocks = cap;
-  group_aggregate_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(a);
+  switch (agg) {
+    case B2P_AGG_SUM: group_aggregate_kernel<B2P_AGG_SUM><<<(unsigned)blocks, 256, 0, c->stream>>>(a); break;
+    case B2P_AGG_AVG: group_aggregate_kernel<B2P_AGG_AVG><<<(unsigned)blocks, 256, 0, c->stream>>>(a); break;
+    case B2P_AGG_COUNT: group_aggregate_kernel<B2P_AGG_COUNT><<<(unsigned)blocks, 256, 0, c->stream>>>(a); break;
+    case B2P_AGG_MIN: group_aggregate_kernel<B2P_AGG_MIN><<<(unsigned)blocks, 256, 0, c->stream>>>(a); break;
+    case B2P_AGG_MAX: group_aggregate_kernel<B2P_AGG_MAX><<<(unsigned)blocks, 256, 0, c->stream>>>(a); break;
+    case B2P_AGG_STDVAR: group_aggregate_kernel<B2P_AGG_STDVAR><<<(unsigned)blocks, 256, 0, c->stream>>>(a); break;
+    default: group_aggregate_kernel<B2P_AGG_STDDEV><<<(unsigned)blocks, 256, 0, c->stream>>>(a); break;
+  }
   c->launches++;
   stage_end(c, 3);
   CU(cudaGetLastError());
   return B2P_OK;
 }
+}  // namespace
 
 int b2p_range_group_sum_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val,
                             const uint64_t* offsets, uint64_t n_rows, uint32_t n_series, const uint32_t* gid,
@@ -717,23 +740,13 @@ int b2p_range_group_sum_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t
   const uint32_t Tw = (uint32_t)((T + 31) / 32);
   if ((rc = c->h_aux0.ensure((size_t)n_series * (size_t)T * 8))) return rc;
   if ((rc = c->h_aux1.ensure((size_t)n_series * Tw * 4))) return rc;
-  if ((rc = c->h_aux2.ensure((size_t)n_groups * (size_t)T * 8))) return rc;
-  if ((rc = c->h_aux3.ensure((size_t)n_groups * (size_t)T * 4))) return rc;
   if ((rc = b2p_range_eval_dev(c, p, ts, val, offsets, n_rows, n_series, c->h_aux0.as<double>(),
                                c->h_aux1.as<uint32_t>())))
     return rc;
   if ((rc = b2p_sync(c))) return rc;  // slow-path fix-ups must land before the aggregate reads
-  if ((rc = b2p_group_aggregate_dev(c, B2P_AGG_SUM, c->h_aux0.as<double>(), c->h_aux1.as<uint32_t>(), gid, n_series,
-                                    n_groups, (uint64_t)T, c->h_aux2.as<double>(), c->h_aux3.as<uint32_t>())))
-    return rc;
-  // out += partial
-  const uint64_t n = (uint64_t)n_groups * (uint64_t)T;
-  uint64_t blocks = (n + 255) / 256;
-  if (blocks > (uint64_t)c->num_sms * 16) blocks = (uint64_t)c->num_sms * 16;
-  accumulate_partials_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(out_sum, out_cnt, c->h_aux2.as<double>(), c->h_aux3.as<uint32_t>(), n);
-  c->launches++;
-  CU(cudaGetLastError());
-  return B2P_OK;
+  // by-label partials added straight into the caller's buffers (K3 in accumulate mode)
+  return group_aggregate_impl(c, B2P_AGG_SUM, c->h_aux0.as<double>(), c->h_aux1.as<uint32_t>(), gid, n_series, n_groups,
+                              (uint64_t)T, out_sum, out_cnt, 1);
 }
 
 int b2p_group_finalize_dev(b2p_ctx* c, int32_t agg, double* val, const uint32_t* cnt, uint64_t n) {
