@@ -203,9 +203,21 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Lea
     // steps past the trimmed end (and past the grid) are never visited by calculate_range: for the cursor
     // bookkeeping they count as empty
     const bool ne = ((int32_t)q <= g) && (!TAIL || k <= kl);
-    const uint32_t ne_mask = __ballot_sync(0xffffffffu, ne);
+    // Short form for the usual miss (a sample exactly on a window edge shifts a few guesses by one): inside the
+    // run of non-empty windows, before the end of the stream, every window non-empty and no window start more
+    // than two samples past its predecessor's.  A cursor start is then lo - 1 + advance <= lo + 1 <= hi + 1 <=
+    // top < m (hi <= top - 1 before the end of the stream), so the exact bookkeeping below cannot object.
+    bool short_form = false;
+    if (!TAIL && st.phase == 1u) {
+      uint32_t prev_q = __shfl_up_sync(0xffffffffu, q, 1);
+      if (lane == 0) prev_q = st.base_lo;
+      short_form = __all_sync(0xffffffffu, ne && (q - prev_q <= 2u));
+    }
+    const uint32_t ne_mask = short_form ? 0u : __ballot_sync(0xffffffffu, ne);
     // empty windows are only tolerated before the first and after the last non-empty one
-    if (ne_mask) {
+    if (short_form) {
+      // phase stays 1: the cursor start handed to the next group is below m as well
+    } else if (ne_mask) {
       const int first = __ffs(ne_mask) - 1, last = 31 - __clz(ne_mask);
       const bool contiguous = (ne_mask >> first) == (0xffffffffu >> (31 - (last - first)));
       if (!contiguous || st.phase == 2u || (st.phase == 1u && first != 0)) return 1;
