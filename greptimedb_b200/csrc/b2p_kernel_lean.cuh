@@ -179,13 +179,22 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Lea
   const uint32_t t_hi1 = acc.t((uint32_t)(g + 1));
   const uint32_t t_lo1 = acc.t(q - 1u);
   uint32_t t_lo = acc.t(q);
-  const bool good = (t_hi <= te) && (t_hi1 > te) && (t_lo1 <= tlo) && (t_lo > tlo) && ((int32_t)q <= g);
+  // steps past the trimmed end (tail groups only) are never visited by calculate_range: their guesses need not hold
+  const bool real = !TAIL || k <= kl;
+  const bool good = !real || ((t_hi <= te) && (t_hi1 > te) && (t_lo1 <= tlo) && (t_lo > tlo) && ((int32_t)q <= g));
   // uniform: the previous step had a non-empty window and no cursor start of this group can reach the end of
   // the series.  A cursor start is lo - 1 + (advance of lo) while a younger sample follows the window: before
   // the end of the stream, with at most one sample of advance per step (d_lo <= 32), that is at most
   // lo <= hi <= top - 1, so verified guesses imply it; otherwise bound it by base_lo + d_lo + ceil(d_lo/32).
   bool uni = st.phase == 1u;
-  if (TAIL || st.d_lo > 32u) uni = uni && (st.base_lo + st.d_lo + ((st.d_lo + 31u) >> 5) < m);
+  if (TAIL) {
+    // only the steps up to the trimmed end count: the largest window start among them plus one step's advance
+    const int32_t n_real = kl - (k - lane) + 1;  // steps of this group that calculate_range visits
+    const uint32_t nr = n_real < 0 ? 0u : (n_real > 32 ? 32u : (uint32_t)n_real);
+    uni = uni && (st.base_lo + ((nr * st.d_lo) >> 5) + ((st.d_lo + 31u) >> 5) < m);
+  } else if (st.d_lo > 32u) {
+    uni = uni && (st.base_lo + st.d_lo + ((st.d_lo + 31u) >> 5) < m);
+  }
   if (uni && __all_sync(0xffffffffu, good)) {
     st.base_hi += (int32_t)st.d_hi;
     st.base_lo += st.d_lo;
