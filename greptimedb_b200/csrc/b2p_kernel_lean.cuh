@@ -506,10 +506,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
           } else if (d < (int64_t)a.rel_max) {
             // last_aligned = trunc((last_ts + range) / interval) * interval, aligned to 0 (not to start);
             // last_ts + range = start + d, so (last_ts + range) mod interval = (start_mod + d) mod interval
+            // both quotients by reciprocal multiply + one correction step (operands < 2^32: the double product
+            // is within 1 of the quotient)
             const uint32_t iv = (uint32_t)a.interval;
             const uint32_t x = a.start_mod + (uint32_t)d;
-            const uint32_t xm = x % iv;
-            kl = ((uint32_t)d >= xm) ? (int32_t)(((uint32_t)d - xm) / iv) : -1;
+            uint32_t qx = (uint32_t)__double2uint_rz((double)x * a.rcp_interval);
+            if ((unsigned long long)qx * iv > x) --qx; else if (x - qx * iv >= iv) ++qx;  // 64-bit: qx*iv < x + iv
+            const uint32_t xm = x - qx * iv;  // x mod iv
+            if ((uint32_t)d >= xm) {
+              const uint32_t y = (uint32_t)d - xm;  // a multiple of iv away from start: last_aligned - start
+              uint32_t qy = (uint32_t)__double2uint_rz((double)y * a.rcp_interval);
+              if ((unsigned long long)qy * iv > y) --qy; else if (y - qy * iv >= iv) ++qy;
+              kl = (int32_t)qy;
+            } else {
+              kl = -1;
+            }
             kl = kl > T - 1 ? T - 1 : kl;
           }
         }
