@@ -345,9 +345,9 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
-                     # captures (2e8-sample launch), scaled: K2L 3.210 + 1.599 GB (profiles/r1_range_lean_kernel.md),
+                     # captures (2e8-sample launch), scaled: K2L 3.214 + 1.599 GB (profiles/r1_range_lean_kernel.md),
                      # K2 alone 3.381 + 1.585 GB (profiles/r1_range_fast_kernel.md, version f)
-                     "traffic": (4.809e9 if lean_on else 4.966e9) * (n_rows / 2.0e8), "peak_source": peak_src,
+                     "traffic": (4.813e9 if lean_on else 4.966e9) * (n_rows / 2.0e8), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_k2, "kernel_ms": k2, "k0_series_offsets_ms": k0,
                      "hbm_read_frac_whole_step": read_frac},
         "gpu_launches": launches, "slow_path_series": slow_series, "warp_tier_series": warp_tier_series, "clocks": clocks,
