@@ -287,17 +287,57 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
   const uint32_t tlo_a = te - rng, tlo_b = te_b - rng;
   acc.set_window((int32_t)st.base_lo - 1);
   if constexpr (FLAGS) acc.no_flags = st.last_flag <= st.base_lo;  // no bit can lie inside a window of this group
-  const int32_t g_a = st.base_hi + (int32_t)((lane1 * st.d_hi) >> 5), g_b = g_a + (int32_t)st.d_hi;
-  const uint32_t q_a = st.base_lo + ((lane1 * st.d_lo) >> 5), q_b = q_a + st.d_lo;
-  const uint32_t t_hi_a = acc.t((uint32_t)g_a), t_hi1_a = acc.t((uint32_t)(g_a + 1));
-  const uint32_t t_lo1_a = acc.t(q_a - 1u), t_lo_a = acc.t(q_a);
-  const uint32_t t_hi_b = acc.t((uint32_t)g_b), t_hi1_b = acc.t((uint32_t)(g_b + 1));
-  const uint32_t t_lo1_b = acc.t(q_b - 1u), t_lo_b = acc.t(q_b);
+  int32_t g_a = st.base_hi + (int32_t)((lane1 * st.d_hi) >> 5), g_b = g_a + (int32_t)st.d_hi;
+  uint32_t q_a = st.base_lo + ((lane1 * st.d_lo) >> 5), q_b = q_a + st.d_lo;
+  uint32_t t_hi_a = acc.t((uint32_t)g_a);
+  const uint32_t t_hi1_a = acc.t((uint32_t)(g_a + 1));
+  const uint32_t t_lo1_a = acc.t(q_a - 1u);
+  uint32_t t_lo_a = acc.t(q_a);
+  uint32_t t_hi_b = acc.t((uint32_t)g_b);
+  const uint32_t t_hi1_b = acc.t((uint32_t)(g_b + 1));
+  const uint32_t t_lo1_b = acc.t(q_b - 1u);
+  uint32_t t_lo_b = acc.t(q_b);
   const bool good = (t_hi_a <= te) && (t_hi1_a > te) && (t_lo1_a <= tlo_a) && (t_lo_a > tlo_a) && ((int32_t)q_a <= g_a) &&
                     (t_hi_b <= te_b) && (t_hi1_b > te_b) && (t_lo1_b <= tlo_b) && (t_lo_b > tlo_b) && ((int32_t)q_b <= g_b);
-  if (!__all_sync(0xffffffffu, good)) return false;
-  st.base_hi += 2 * (int32_t)st.d_hi;
-  st.base_lo += 2u * st.d_lo;
+  if (__all_sync(0xffffffffu, good)) {
+    st.base_hi += 2 * (int32_t)st.d_hi;
+    st.base_lo += 2u * st.d_lo;
+  } else {
+    // Repair in place (the usual miss: a sample exactly on a window edge shifts a few guesses by one): every lane
+    // walks both steps to their definitional edges — the newest sample is younger than both window ends and slot
+    // base_lo - 1 / the -1 sentinel bound the walks — and the pair goes on if the short form of lean_group holds
+    // for all 64 steps (non-empty windows, at most two samples of advance per step => every cursor start is
+    // <= lo + 1 <= top < m).  Nothing of the warp state has been touched yet, so "false" still means "one at a time".
+    while (acc.t((uint32_t)(g_a + 1)) <= te) ++g_a;
+    while (acc.t((uint32_t)g_a) > te) --g_a;
+    q_a = q_a > (uint32_t)(g_a + 1) ? (uint32_t)(g_a + 1) : q_a;
+    while (acc.t(q_a - 1u) > tlo_a) --q_a;
+    while (acc.t(q_a) <= tlo_a) ++q_a;
+    while (acc.t((uint32_t)(g_b + 1)) <= te_b) ++g_b;
+    while (acc.t((uint32_t)g_b) > te_b) --g_b;
+    q_b = q_b > (uint32_t)(g_b + 1) ? (uint32_t)(g_b + 1) : q_b;
+    while (acc.t(q_b - 1u) > tlo_b) --q_b;
+    while (acc.t(q_b) <= tlo_b) ++q_b;
+    uint32_t prev_a = __shfl_up_sync(0xffffffffu, q_a, 1);
+    uint32_t prev_b = __shfl_up_sync(0xffffffffu, q_b, 1);
+    const uint32_t last_a = __shfl_sync(0xffffffffu, q_a, 31);
+    if (lane == 0) {
+      prev_a = st.base_lo;
+      prev_b = last_a;
+    }
+    const bool fine = ((int32_t)q_a <= g_a) && ((int32_t)q_b <= g_b) && (q_a - prev_a <= 2u) && (q_b - prev_b <= 2u);
+    if (!__all_sync(0xffffffffu, fine)) return false;
+    t_hi_a = acc.t((uint32_t)g_a);
+    t_lo_a = acc.t(q_a);
+    t_hi_b = acc.t((uint32_t)g_b);
+    t_lo_b = acc.t(q_b);
+    const int32_t nhi = __shfl_sync(0xffffffffu, g_b, 31);
+    const uint32_t nlo = __shfl_sync(0xffffffffu, q_b, 31);
+    st.d_hi = (uint32_t)(nhi - st.base_hi + 1) >> 1;  // advance per group over the 64 steps
+    st.d_lo = (nlo - st.base_lo + 1u) >> 1;
+    st.base_hi = nhi;
+    st.base_lo = nlo;
+  }
   bool ok_a, ok_b;
   const double r_a = lean_value<FN, FLAGS>(a, acc, g_a, q_a, t_lo_a, t_hi_a, te, ok_a);
   out_p[0] = r_a;
