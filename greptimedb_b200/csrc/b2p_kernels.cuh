@@ -156,7 +156,10 @@ __global__ void __launch_bounds__(256) series_offsets_kernel(const uint32_t* __r
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t cur = v[j][i] - sid_base;
-        if (i < cnt[j]) offsets_scan_one(cur, prev, r0 + i, n_rows, n_series, offsets, status);
+        // only the row where the id changes (or the first / last row of the column) has anything to do; an id
+        // equal to its predecessor was range-checked where it first appeared
+        if (i < cnt[j] && (cur != prev || r0 + i == 0 || r0 + i == n_rows - 1))
+          offsets_scan_one(cur, prev, r0 + i, n_rows, n_series, offsets, status);
         prev = cur;
       }
     }
