@@ -131,14 +131,6 @@ __global__ void __launch_bounds__(256) group_finalize_kernel(int32_t agg, double
   }
 }
 
-__global__ void __launch_bounds__(256) accumulate_partials_kernel(double* o, uint32_t* oc, const double* a,
-                                                                  const uint32_t* ac, uint64_t n) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    o[i] += a[i];
-    oc[i] += ac[i];
-  }
-}
-
 __global__ void __launch_bounds__(256) iota_kernel(uint32_t* p, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
 }
