@@ -705,7 +705,7 @@ def _fuzz_series(rng, n_series):
     return np.concatenate(ts_l), np.concatenate(val_l), np.array(offs, np.uint64), t_base
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(24))
 def test_fuzz_random_queries_match_oracle(ctx, ctx_thread_tier, ctx_no_lean, ctx_lean_flags, seed):
     """Random series zoo x random (start, end, interval, range, offset): validity bit-exact, values <= 1e-9 rel."""
     from greptimedb_b200 import make_params
