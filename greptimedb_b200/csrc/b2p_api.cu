@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -72,6 +73,8 @@ struct DevBuf {
 };
 
 constexpr int kRing = 256;
+constexpr int kBigRing = 1024;        // long-window instantiation of the warp-per-series kernel (one CTA per SM)
+constexpr int kStatusSlots = 32;      // range calls that may be outstanding between two b2p_sync
 constexpr int kSlowCtas = 148;        // slow-path grid (4 warps per CTA)
 constexpr int kSlowWarps = kSlowCtas * 4;
 constexpr size_t kArenaDefaultRows = 1u << 20;
@@ -82,9 +85,19 @@ struct b2p_ctx {
   int device = 0;
   int num_sms = 148;
   cudaStream_t own_stream = nullptr, stream = nullptr;
-  Status* d_status = nullptr;
-  Status* h_status = nullptr;  // pinned mirror
-  DevBuf slow_list, w_list, arena_ts, arena_val, win_scratch;
+  // Device-side status.  Every range call owns one slot of d_ring until b2p_sync has read it back, so any number
+  // (<= kStatusSlots, then the library synchronises by itself) of *_dev range calls may be outstanding; the verdict
+  // of the series-id scan (K0) is sticky in d_k0 until the next b2p_sync.
+  Status* d_ring = nullptr;  // [kStatusSlots]
+  Status* h_ring = nullptr;  // pinned mirror
+  Status* d_k0 = nullptr;
+  Status* h_k0 = nullptr;    // pinned
+  int next_slot = 0;
+  struct Pending {
+    int slot; int fn; RangeArgs args; int lean_mode; bool thread_tier; bool used_lean; uint32_t n_series; bool verdict_taken;
+  };
+  std::vector<Pending> pending;
+  DevBuf slow_list, w_list, b_list, arena_ts, arena_val, win_scratch;
   // K2T (thread per series) in front of K2 for rate/increase/delta.  Measured slower than K2 on B200
   // (28 vs 64 G samples/s, profiles/r1_thread_tier.md), so it is opt-in: B2P_ENABLE_THREAD_TIER=1.
   bool thread_tier = false;
@@ -107,10 +120,6 @@ struct b2p_ctx {
   cudaEvent_t ev[4][2] = {};
   bool ev_used[4] = {false, false, false, false};
   long long launches = 0;
-  // last range call, kept so b2p_sync can re-run the slow path after growing the arena
-  RangeArgs last_args{};
-  int last_fn = -1;
-  bool pending_range = false;
   long long last_slow = 0;
   long long last_w = 0;
   // host-API staging
@@ -125,6 +134,7 @@ struct b2p_ctx {
   // column reduce scratch
   DevBuf c_psum, c_pcnt;
   int fast_blocks_per_sm[B2P_FN__COUNT][2] = {};
+  int big_blocks_per_sm[B2P_FN__COUNT] = {};
 };
 
 namespace {
@@ -166,6 +176,26 @@ int launch_fast_t(b2p_ctx* c, const RangeArgs& a) {
   const unsigned grid = need < cap ? need : cap;
   if (grid == 0) return B2P_OK;
   kern<<<grid, kWarpsPerCta * 32, smem, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+// Long-window instantiation (32-bit time domain only): RING = kBigRing, one CTA per SM, over RangeArgs::b_list.
+template <int FN>
+int launch_big(b2p_ctx* c, const RangeArgs& a0) {
+  RangeArgs a = a0;
+  a.use_w_list = 2;
+  constexpr size_t smem = (size_t)kWarpsPerCta * (2 * kBigRing * (8 + 4) + kBigRing / 8) + kRcpTable * 8;
+  auto kern = range_fast_kernel<FN, kBigRing, true>;
+  int& cached = c->big_blocks_per_sm[FN];
+  if (cached == 0) {
+    int nb = 0;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarpsPerCta * 32, smem));
+    cached = nb > 0 ? nb : 1;
+  }
+  kern<<<(unsigned)(c->num_sms * cached), kWarpsPerCta * 32, smem, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
   return B2P_OK;
@@ -218,8 +248,7 @@ bool lean_ok(const b2p_ctx* c, int fn, const RangeArgs& a);
 
 template <int FN, bool FLAGS>
 int launch_lean(b2p_ctx* c, const RangeArgs& a) {
-  constexpr size_t smem = (size_t)kWarpsPerCta * kLeanRing * 16 + kRcpTable * 8 + (size_t)kWarpsPerCta * 2 * 64 * 16 +
-                          (size_t)kWarpsPerCta * (kLeanRing / 32) * 4;
+  constexpr size_t smem = lean_smem_bytes();
   auto kern = range_lean_kernel<FN, FLAGS>;
   int& cached = c->lean_blocks_per_sm[FN][FLAGS ? 1 : 0];
   if (cached == 0) {
@@ -306,6 +335,14 @@ int dispatch_fast(b2p_ctx* c, int fn, const RangeArgs& a) {
   }
   return fail(B2P_E_INVALID, "unknown fn_id %d", fn);
 }
+int dispatch_big(b2p_ctx* c, int fn, const RangeArgs& a) {
+  switch (fn) {
+#define X(N) case N: return launch_big<N>(c, a);
+    B2P_FOR_EACH_FN(X)
+#undef X
+  }
+  return fail(B2P_E_INVALID, "unknown fn_id %d", fn);
+}
 int dispatch_slow(b2p_ctx* c, int fn, const RangeArgs& a) {
   switch (fn) {
 #define X(N) case N: return launch_slow<N>(c, a);
@@ -339,15 +376,13 @@ int check_grid(const b2p_range_params* p, uint32_t n_series, int64_t* T_out) {
   return B2P_OK;
 }
 
-int reset_status(b2p_ctx* c) {
-  CU(cudaMemsetAsync(c->d_status, 0, sizeof(Status), c->stream));
-  return B2P_OK;
-}
+int reset_status(b2p_ctx*) { return B2P_OK; }  // (every range call resets its own status slot; K0's verdict is sticky)
 
 int ensure_slow_scratch(b2p_ctx* c, uint32_t n_series, int64_t T) {
   int rc;
   if ((rc = c->slow_list.ensure((size_t)(n_series ? n_series : 1) * 4))) return rc;
   if ((rc = c->w_list.ensure((size_t)(n_series ? n_series : 1) * 4))) return rc;
+  if ((rc = c->b_list.ensure((size_t)(n_series ? n_series : 1) * 4))) return rc;
   if ((rc = c->win_scratch.ensure((size_t)kSlowWarps * (size_t)(T > 0 ? T : 1) * 8))) return rc;
   if (c->arena_rows == 0) {
     if ((rc = c->arena_ts.ensure(kArenaDefaultRows * 8))) return rc;
@@ -392,8 +427,10 @@ b2p_ctx* b2p_create(int device) {
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
   bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   c->stream = c->own_stream;
-  ok = ok && cudaMalloc(&c->d_status, sizeof(Status)) == cudaSuccess;
-  ok = ok && cudaMallocHost(&c->h_status, sizeof(Status)) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_ring, kStatusSlots * sizeof(Status)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&c->h_ring, kStatusSlots * sizeof(Status)) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_k0, sizeof(Status)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&c->h_k0, sizeof(Status)) == cudaSuccess;
   for (int i = 0; ok && i < 4; ++i)
     for (int j = 0; j < 2; ++j) ok = ok && cudaEventCreate(&c->ev[i][j]) == cudaSuccess;
   if (!ok) {
@@ -401,7 +438,8 @@ b2p_ctx* b2p_create(int device) {
     b2p_destroy(c);
     return nullptr;
   }
-  cudaMemset(c->d_status, 0, sizeof(Status));
+  cudaMemset(c->d_ring, 0, kStatusSlots * sizeof(Status));
+  cudaMemset(c->d_k0, 0, sizeof(Status));
   {
     double tab[kRcpTable];
     tab[0] = 0.0;
@@ -423,7 +461,7 @@ void b2p_destroy(b2p_ctx* c) {
   if (!c) return;
   DeviceGuard g(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-  for (DevBuf* b : {&c->slow_list, &c->w_list, &c->arena_ts, &c->arena_val, &c->win_scratch, &c->h_ts, &c->h_val, &c->h_sid,
+  for (DevBuf* b : {&c->slow_list, &c->w_list, &c->b_list, &c->arena_ts, &c->arena_val, &c->win_scratch, &c->h_ts, &c->h_val, &c->h_sid,
                     &c->h_off, &c->h_out, &c->h_valid, &c->h_aux0, &c->h_aux1, &c->h_aux2, &c->h_aux3,
                     &c->g_keys_in, &c->g_keys_out, &c->g_vals_in, &c->g_vals_out, &c->g_goff, &c->g_tmp, &c->c_psum,
                     &c->c_pcnt})
@@ -440,8 +478,10 @@ void b2p_destroy(b2p_ctx* c) {
   c->p_status.release();
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
-  if (c->d_status) cudaFree(c->d_status);
-  if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->d_ring) cudaFree(c->d_ring);
+  if (c->h_ring) cudaFreeHost(c->h_ring);
+  if (c->d_k0) cudaFree(c->d_k0);
+  if (c->h_k0) cudaFreeHost(c->h_k0);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -473,40 +513,78 @@ double b2p_last_kernel_ms(b2p_ctx* c, int stage) {
   return (double)ms;
 }
 
+// Launches every tier of one range call (first tier when `used_lean`/`thread_tier`, warp-per-series kernel, its
+// long-window instantiation, exact slow kernel) on the context's stream.
+static int launch_range_tiers(b2p_ctx* c, int fn, RangeArgs a, bool thread_tier, bool used_lean, int lean_mode) {
+  int rc;
+  CU(cudaMemsetAsync(a.status, 0, sizeof(Status), c->stream));
+  stage_begin(c, 1);
+  if (thread_tier) {
+    if (fn == B2P_FN_RATE) rc = launch_thread_tier<B2P_FN_RATE>(c, a);
+    else if (fn == B2P_FN_INCREASE) rc = launch_thread_tier<B2P_FN_INCREASE>(c, a);
+    else rc = launch_thread_tier<B2P_FN_DELTA>(c, a);
+    if (rc) return rc;
+    a.use_w_list = 1;
+  } else if (used_lean) {
+    if ((rc = dispatch_lean(c, fn, a, lean_mode == 1))) return rc;
+    a.use_w_list = 1;
+  }
+  rc = dispatch_fast(c, fn, a);
+  if (!rc && a.b_list) rc = dispatch_big(c, fn, a);
+  stage_end(c, 1);
+  if (rc) return rc;
+  stage_begin(c, 2);
+  rc = dispatch_slow(c, fn, a);
+  stage_end(c, 2);
+  return rc;
+}
+
 int b2p_sync(b2p_ctx* c) {
   if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
   DeviceGuard g(c->device);
-  for (int attempt = 0; attempt < 3; ++attempt) {
-    CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(Status), cudaMemcpyDeviceToHost, c->stream));
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    CU(cudaMemcpyAsync(c->h_ring, c->d_ring, kStatusSlots * sizeof(Status), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_k0, c->d_k0, sizeof(Status), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    const Status st = *c->h_status;
-    c->last_slow = st.slow_count;
-    c->last_w = st.w_count;
-    if (c->pending_range && c->last_used_lean) lean_verdict(c, c->last_range_fn, st.w_count, c->last_range_series);
-    if (st.k0_errors & 1u) return fail(B2P_E_UNSORTED, "series-id column is not non-decreasing");
-    if (st.k0_errors & 2u) return fail(B2P_E_UNSORTED, "series id >= n_series");
-    if (!st.arena_overflow) {
-      c->pending_range = false;
-      return B2P_OK;
+    const uint32_t k0 = c->h_k0->k0_errors;
+    if (k0) {
+      CU(cudaMemsetAsync(c->d_k0, 0, sizeof(Status), c->stream));
+      c->pending.clear();
+      if (k0 & 1u) return fail(B2P_E_UNSORTED, "series-id column is not non-decreasing");
+      return fail(B2P_E_UNSORTED, "series id >= n_series");
     }
-    // slow-path arena too small: grow it and re-run only the slow kernel (the work list is intact)
-    if (!c->pending_range) return fail(B2P_E_NOMEM, "slow-path arena overflow with no pending call");
-    const size_t need = (size_t)st.arena_needed + 1024;
+    // verdicts of the outstanding range calls, oldest first; a call whose slow path ran out of arena is redone
+    // as a whole (all tiers, same modes) after the arena has grown to what the largest of them needs
+    size_t need = 0;
+    std::vector<b2p_ctx::Pending> redo;
+    for (auto& pc : c->pending) {
+      const Status st = c->h_ring[pc.slot];
+      c->last_slow = st.slow_count;
+      c->last_w = st.w_count;
+      if (pc.used_lean && !pc.verdict_taken) {
+        c->last_lean_mode = pc.lean_mode;
+        lean_verdict(c, pc.fn, st.w_count, pc.n_series);
+        pc.verdict_taken = true;
+      }
+      if (st.arena_overflow) {
+        if ((size_t)st.arena_needed + 1024 > need) need = (size_t)st.arena_needed + 1024;
+        redo.push_back(pc);
+      }
+    }
+    c->pending.clear();
+    if (redo.empty()) return B2P_OK;
     int rc;
     if ((rc = c->arena_ts.ensure(need * 8))) return rc;
     if ((rc = c->arena_val.ensure(need * 8))) return rc;
     c->arena_rows = need;
-    c->last_args.arena_ts = c->arena_ts.as<int64_t>();
-    c->last_args.arena_val = c->arena_val.as<double>();
-    c->last_args.arena_cap = need;
-    Status patch = st;
-    patch.arena_overflow = 0;
-    patch.arena_used = 0;
-    patch.arena_needed = 0;
-    *c->h_status = patch;
-    CU(cudaMemcpyAsync(c->d_status, c->h_status, sizeof(Status), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if ((rc = dispatch_slow(c, c->last_fn, c->last_args))) return rc;
+    for (auto& pc : redo) {
+      pc.args.arena_ts = c->arena_ts.as<int64_t>();
+      pc.args.arena_val = c->arena_val.as<double>();
+      pc.args.arena_cap = need;
+      if ((rc = launch_range_tiers(c, pc.fn, pc.args, pc.thread_tier, pc.used_lean, pc.lean_mode))) return rc;
+      c->pending.push_back(pc);
+      CU(cudaStreamSynchronize(c->stream));  // one redone call at a time: they share the arena from offset 0
+    }
   }
   return fail(B2P_E_NOMEM, "slow-path arena could not be sized");
 }
@@ -529,9 +607,8 @@ static int series_offsets_impl(b2p_ctx* c, const uint32_t* sid, uint64_t n_rows,
   const uint64_t cap = (uint64_t)c->num_sms * 16;
   if (blocks > cap) blocks = cap;
   if (blocks == 0) blocks = 1;
-  CU(cudaMemsetAsync(&c->d_status->k0_errors, 0, sizeof(uint32_t), c->stream));
   stage_begin(c, 0);
-  series_offsets_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(sid, n_rows, n_series, sid_base, offsets, c->d_status);
+  series_offsets_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(sid, n_rows, n_series, sid_base, offsets, c->d_k0);
   c->launches++;
   stage_end(c, 0);
   CU(cudaGetLastError());
@@ -570,51 +647,40 @@ int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts,
   }
   a.ts = ts; a.val = val; a.offsets = offsets; a.n_rows = n_rows; a.n_series = n_series;
   a.out = out; a.valid = valid_words;
-  a.status = c->d_status; a.slow_list = c->slow_list.as<uint32_t>();
+  // every call owns a status slot until b2p_sync has read it; with all slots taken the library synchronises itself
+  if ((int)c->pending.size() >= kStatusSlots && (rc = b2p_sync(c))) return rc;
+  const int slot = c->next_slot;
+  c->next_slot = (c->next_slot + 1) % kStatusSlots;
+  a.status = c->d_ring + slot; a.slow_list = c->slow_list.as<uint32_t>();
   a.w_list = c->w_list.as<uint32_t>();
+  a.b_list = fits_ts32(a) ? c->b_list.as<uint32_t>() : nullptr;  // long windows: the 1024-sample ring (32-bit domain)
   a.use_w_list = 0;
   a.arena_ts = c->arena_ts.as<int64_t>(); a.arena_val = c->arena_val.as<double>(); a.arena_cap = c->arena_rows;
   a.win_scratch = c->win_scratch.as<unsigned long long>();
-  // the status block also carries K0's verdict; only the slow-path fields are reset here
-  CU(cudaMemsetAsync(&c->d_status->slow_count, 0, 2 * sizeof(uint32_t), c->stream));
-  CU(cudaMemsetAsync(&c->d_status->w_count, 0, sizeof(uint32_t), c->stream));
-  CU(cudaMemsetAsync(&c->d_status->arena_used, 0, 2 * sizeof(unsigned long long), c->stream));
-  stage_begin(c, 1);
-  // tier 1 (rate / increase / delta, 32-bit time domain): thread per series; what it declines goes to
-  // tier 2 (warp per series) through w_list, and what that declines to the exact slow kernel
+  // tier 1 (rate / increase / delta, 32-bit time domain): thread per series (opt-in) or the lean warp-per-series
+  // kernel; what it declines goes to tier 2 (warp per series) through w_list, long windows from there to the
+  // 1024-sample instantiation through b_list, and what that declines to the exact slow kernel
   const bool tier1 = c->thread_tier && fits_ts32(a) &&
                      (p->fn_id == B2P_FN_RATE || p->fn_id == B2P_FN_INCREASE || p->fn_id == B2P_FN_DELTA);
-  if (tier1) {
-    if (p->fn_id == B2P_FN_RATE) rc = launch_thread_tier<B2P_FN_RATE>(c, a);
-    else if (p->fn_id == B2P_FN_INCREASE) rc = launch_thread_tier<B2P_FN_INCREASE>(c, a);
-    else rc = launch_thread_tier<B2P_FN_DELTA>(c, a);
-    if (rc) return rc;
-    a.use_w_list = 1;
-  } else if (lean_ok(c, p->fn_id, a)) {
-    int mode = 0;
+  bool used_lean = false;
+  int mode = 0;
+  if (!tier1 && lean_ok(c, p->fn_id, a)) {
     if (c->lean_backoff[p->fn_id] > 0) {
       c->lean_backoff[p->fn_id]--;
       mode = c->lean_mode[p->fn_id];
     }
-    c->last_lean_mode = mode;
-    if (mode != 2) {
-      if ((rc = dispatch_lean(c, p->fn_id, a, mode == 1 || c->lean_force_flags))) return rc;
-      a.use_w_list = 1;
-    }
+    if (mode != 2) used_lean = true;
+    if (mode == 0 && c->lean_force_flags) mode = 1;
   }
-  c->last_used_lean = a.use_w_list != 0 && !tier1;
+  c->last_lean_mode = mode;
+  c->last_used_lean = used_lean;
   c->last_range_series = n_series;
   c->last_range_fn = p->fn_id;
-  rc = dispatch_fast(c, p->fn_id, a);
-  stage_end(c, 1);
-  if (rc) return rc;
-  stage_begin(c, 2);
-  rc = dispatch_slow(c, p->fn_id, a);
-  stage_end(c, 2);
-  if (rc) return rc;
-  c->last_args = a;
-  c->last_fn = p->fn_id;
-  c->pending_range = true;
+  if ((rc = launch_range_tiers(c, p->fn_id, a, tier1, used_lean, mode))) return rc;
+  b2p_ctx::Pending pc{};
+  pc.slot = slot; pc.fn = p->fn_id; pc.args = a; pc.lean_mode = mode; pc.thread_tier = tier1; pc.used_lean = used_lean;
+  pc.n_series = n_series; pc.verdict_taken = false;
+  c->pending.push_back(pc);
   return B2P_OK;
 }
 
@@ -883,6 +949,7 @@ int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, con
   if (!sid && !offsets_host) return fail(B2P_E_INVALID, "need sid or offsets_host");
   if (!out || !valid_words || ((!ts || !val) && n_rows)) return fail(B2P_E_INVALID, "NULL argument");
   DeviceGuard g(c->device);
+  if (!c->pending.empty() && (rc = b2p_sync(c))) return rc;  // earlier asynchronous calls finish first
   const uint32_t Tw = (uint32_t)((T + 31) / 32);
 
   // ---- small inputs: one shot -------------------------------------------------------------------
@@ -970,7 +1037,11 @@ int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, con
     if ((rc = b2p_range_eval_dev(c, p, c->p_ts[b].as<int64_t>(), c->p_val[b].as<double>(), c->p_off[b].as<uint64_t>(),
                                  nr, ns, c->p_out[b].as<double>(), c->p_valid[b].as<uint32_t>())))
       return rc;
-    CU(cudaMemcpyAsync(c->p_status.as<Status>() + i, c->d_status, sizeof(Status), cudaMemcpyDeviceToDevice, c->stream));
+    {  // this chunk's verdict is read with all the others below: take the call out of the pending queue
+      const int slot = c->pending.back().slot;
+      c->pending.pop_back();
+      CU(cudaMemcpyAsync(c->p_status.as<Status>() + i, c->d_ring + slot, sizeof(Status), cudaMemcpyDeviceToDevice, c->stream));
+    }
     CU(cudaEventRecord(c->ev_comp[b], c->stream));
     // D2H
     CU(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[b], 0));
@@ -982,9 +1053,14 @@ int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, con
     row_lo = row_hi;
   }
   CU(cudaMemcpyAsync(h_stat, c->p_status.p, (size_t)n_chunks * sizeof(Status), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_k0, c->d_k0, sizeof(Status), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaStreamSynchronize(c->s_d2h));
-  c->pending_range = false;
+  if (const uint32_t k0 = c->h_k0->k0_errors) {
+    CU(cudaMemsetAsync(c->d_k0, 0, sizeof(Status), c->stream));
+    if (k0 & 1u) return fail(B2P_E_UNSORTED, "series-id column is not non-decreasing");
+    return fail(B2P_E_UNSORTED, "series id >= n_series");
+  }
   // per-chunk verdicts; a chunk whose slow path ran out of arena is redone alone (b2p_sync grows the arena)
   long long slow_total = 0, w_total = 0;
   row_lo = 0;
@@ -995,8 +1071,6 @@ int b2p_range_eval(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, con
     const Status st = h_stat[i];
     slow_total += st.slow_count;
     w_total += st.w_count;
-    if (st.k0_errors & 1u) return fail(B2P_E_UNSORTED, "series-id column is not non-decreasing");
-    if (st.k0_errors & 2u) return fail(B2P_E_UNSORTED, "series id >= n_series");
     if (st.arena_overflow) {
       std::string tmp_offs;
       const uint64_t* offs_chunk = nullptr;

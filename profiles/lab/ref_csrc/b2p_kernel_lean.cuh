@@ -37,12 +37,6 @@ namespace b2p {
 #define B2P_LEAN_MIN_BLOCKS 3
 #endif
 constexpr int kLeanRing = 256;
-// dynamic shared memory of one CTA: value ring + mirrored timestamp ring + reciprocal table + staging (two 64-row
-// blocks per warp and column) + bit words
-constexpr size_t lean_smem_bytes() {
-  return (size_t)kWarpsPerCta * kLeanRing * 16 + kRcpTable * 8 + (size_t)kWarpsPerCta * 2 * 64 * 16 +
-         (size_t)kWarpsPerCta * (kLeanRing / 32) * 4;
-}
 
 // The per-warp sample ring of this tier.  Timestamps (uint32 ms since start - range) are stored twice, slot p
 // and slot p + RING, so the edge reads around an index need no wrap handling after set_window(); values are

@@ -31,9 +31,7 @@ struct Status {
   uint32_t slow_count;      // series deferred to the slow path          (reset per range call)
   uint32_t arena_overflow;  // slow-path arena too small                 (reset per range call)
   uint32_t k0_errors;       // bit0: sid not sorted, bit1: sid >= n_series (reset per K0 call)
-  uint32_t w_count;         // series the first tier handed to the warp-per-series kernel
-  uint32_t b_count;         // series the warp-per-series kernel handed to its long-window (big ring) instantiation
-  uint32_t pad_;
+  uint32_t w_count;         // series the thread-per-series tier handed to the warp-per-series kernel
   unsigned long long arena_used;    // rows claimed in the slow-path arena
   unsigned long long arena_needed;  // rows that would have been needed
 };
@@ -63,8 +61,7 @@ struct RangeArgs {
   uint32_t* valid;
   // tier hand-off: when use_w_list != 0 the warp-per-series kernel only runs the series in w_list
   uint32_t* w_list;
-  int32_t use_w_list;  // 0: all series; 1: the series in w_list (w_count); 2: the series in b_list (b_count)
-  uint32_t* b_list;    // long-window hand-off: series whose windows do not fit the 256-sample ring
+  int32_t use_w_list;
   // slow path plumbing
   Status* status;
   uint32_t* slow_list;
@@ -504,11 +501,8 @@ __device__ __forceinline__ void process_group_full(const RangeArgs& a, SeriesSta
   st.base_lo = nlo;
 }
 
-// BIG: the long-window instantiation (RING = 1024, one CTA per SM): runs over b_list, hands what even that ring
-// cannot hold to the slow kernel.  The standard instantiation hands ring pressure to b_list when the host enabled
-// it (a.b_list != nullptr), else to the slow kernel like the cursor-overshoot quirk.
 template <int FN, int RING, bool TS32>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (RING > 256 ? 1 : B2P_FAST_MIN_BLOCKS)) range_fast_kernel(const RangeArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_FAST_MIN_BLOCKS) range_fast_kernel(const RangeArgs a) {
   using TD = TimeDom<TS32>;
   using time_type = typename TD::type;
   constexpr int FW = RING / 32;
@@ -527,9 +521,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (RING > 256 ? 1 : B2P_FAST_
   const uint32_t total_warps = gridDim.x * kWarpsPerCta;
   const int32_t T = (int32_t)a.T;
 
-  const uint32_t n_work = a.use_w_list == 2 ? a.status->b_count : (a.use_w_list ? a.status->w_count : a.n_series);
+  const uint32_t n_work = a.use_w_list ? a.status->w_count : a.n_series;
   for (uint32_t wi = blockIdx.x * kWarpsPerCta + warp; wi < n_work; wi += total_warps) {
-    const uint32_t s = a.use_w_list == 2 ? a.b_list[wi] : (a.use_w_list ? a.w_list[wi] : wi);
+    const uint32_t s = a.use_w_list ? a.w_list[wi] : wi;
     const uint64_t row0 = a.offsets[s], row1 = a.offsets[s + 1];
     double* const out_s = a.out + (size_t)s * (size_t)T;
     uint32_t* const vw_s = a.valid + (size_t)s * a.Tw;
@@ -542,14 +536,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (RING > 256 ? 1 : B2P_FAST_
     int64_t last_ts = 0;  // exact (absolute, offset applied) timestamp of the newest surviving sample
     int32_t k_fin = 0;    // steps [0, k_fin) can be evaluated with what is in the ring
     bool defer = false;
-    bool defer_ring = false;  // the reason is ring pressure (a longer ring can take the series)
 
     // evaluate [k_next, upto) in aligned groups of 32; advances the output cursors
 #define B2P_RUN_STEPS(UPTO, KL)                                                                      \
     do {                                                                                              \
       const int32_t upto__ = (UPTO);                                                                  \
       while (st.k_next < upto__) {                                                                    \
-        if (st.j_cnt - st.base_lo > (uint32_t)(RING - 32)) { defer = true; defer_ring = true; break; } \
+        if (st.j_cnt - st.base_lo > (uint32_t)(RING - 32)) { defer = true; break; }                   \
         int32_t g_end = (st.k_next | 31) + 1;                                                         \
         if (g_end > upto__) g_end = upto__;                                                           \
         if (g_end - st.k_next == 32 && st.k_next >= st.kf && g_end - 1 <= (KL) && st.j_cnt > 0)       \
@@ -672,7 +665,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (RING > 256 ? 1 : B2P_FAST_
             if (adv < 32u) break;
           }
           if ((int32_t)st.base_lo - 1 > st.base_hi) st.base_hi = (int32_t)st.base_lo - 1;
-          if (st.j_cnt + 64u - st.base_lo > (uint32_t)(RING - 32)) { defer = true; defer_ring = true; }
+          if (st.j_cnt + 64u - st.base_lo > (uint32_t)(RING - 32)) defer = true;
         }
       }
     }
@@ -700,13 +693,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (RING > 256 ? 1 : B2P_FAST_
       }
     }
     if (defer && lane == 0) {
-      if (RING <= 256 && defer_ring && a.b_list != nullptr) {
-        const uint32_t i = atomicAdd(&a.status->b_count, 1u);
-        a.b_list[i] = s;
-      } else {
-        const uint32_t i = atomicAdd(&a.status->slow_count, 1u);
-        a.slow_list[i] = s;
-      }
+      const uint32_t i = atomicAdd(&a.status->slow_count, 1u);
+      a.slow_list[i] = s;
     }
     __syncwarp();
   }

@@ -528,6 +528,63 @@ def test_long_windows_overflow_the_ring_and_still_match(ctx):
                      bit_exact=fn == "resets")
 
 
+def test_hour_long_windows_take_the_big_ring_not_the_slow_path(ctx):
+    """rate(x[1h]) at a 15 s scrape holds 240 samples per window: too many for the 256-sample ring next to a 64-row
+    block, so the warp-per-series kernel hands the series to its 1024-sample instantiation (only the
+    cursor-overshoot quirk and windows beyond that ring should reach the serial slow kernel)."""
+    from greptimedb_b200 import make_params
+    S, N, T0 = 64, 1500, 1_700_000_000_000
+    ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, 1000, 1, 7)
+    val[5::211] = np.nan
+    offsets = np.arange(S + 1, dtype=np.uint64) * N
+    for fn in ("rate", "sum_over_time", "resets", "quantile_over_time", "deriv"):
+        p0, p1 = FN_PARAMS.get(fn, (0.0, 0.0))
+        p = make_params(fn, T0, T0 + (N - 1) * 15_000, 60_000, 3_600_000, param0=p0, param1=p1)
+        out, valid, ets = ctx.range_eval(p, ts, val, offsets=offsets)
+        assert ctx.last_slow_series() == 0, fn
+        op = orc.make_params(fn, T0, T0 + (N - 1) * 15_000, 60_000, 3_600_000, param0=p0, param1=p1)
+        e_out, e_valid = orc.range_query(op, ts, val, None, offsets, threads=4)
+        assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size), fn,
+                     bit_exact=fn in BIT_EXACT)
+
+
+def test_several_outstanding_range_calls_each_keep_their_slow_path_verdict(ctx):
+    """*_dev range calls are asynchronous and several may be outstanding; a call whose slow path
+    ran out of arena must not be forgotten when the next call starts.  Three calls, the first and the last with
+    windows far longer than any ring (slow path, arena overflow), one b2p_sync at the end."""
+    import torch
+    from greptimedb_b200 import Context, make_params
+    dev = torch.device("cuda:0")
+    c = Context(0)   # a fresh context: default 1 M-row arena
+    try:
+        S, N, T0 = 1500, 1000, 1_700_000_000_000
+        ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, 1000, 0, 3)
+        offsets = np.arange(S + 1, dtype=np.uint64) * N
+        d_ts, d_val = torch.from_numpy(ts).to(dev), torch.from_numpy(val).to(dev)
+        d_off = torch.from_numpy(offsets.astype(np.int64)).to(dev)
+        queries = [("sum_over_time", 1_500_000, 6_000_000 * 4), ("rate", 15_000, 300_000), ("avg_over_time", 750_000, 6_000_000 * 4)]
+        outs = []
+        c.use_own_stream()
+        torch.cuda.synchronize()
+        for fn, step, rng in queries:
+            p = make_params(fn, T0, T0 + (N - 1) * 15_000, step, rng)
+            T = (999 * 15_000) // step + 1
+            out = torch.full((S * T,), -1.0, dtype=torch.float64, device=dev)
+            valid = torch.full((S * ((T + 31) // 32),), -1, dtype=torch.int32, device=dev)
+            c.range_eval_dev(p, d_ts, d_val, d_off, S * N, S, out, valid)
+            outs.append((fn, step, rng, T, out, valid))
+        c.sync()
+        assert c.last_slow_series() == S   # the last call: every series took the slow path
+        for fn, step, rng, T, out, valid in outs:
+            op = orc.make_params(fn, T0, T0 + (N - 1) * 15_000, step, rng)
+            e_out, e_valid = orc.range_query(op, ts, val, None, offsets, threads=8)
+            g_out = out.cpu().numpy().reshape(S, T)
+            g_valid = valid.cpu().numpy().view(np.uint32).reshape(S, (T + 31) // 32)
+            assert_close(g_out, e_out, orc.valid_to_bool(g_valid, T), orc.valid_to_bool(e_valid, T), f"outstanding {fn}")
+    finally:
+        c.close()
+
+
 def test_series_offsets_from_sid_and_unsorted_error(ctx):
     from greptimedb_b200 import B2PError, make_params
     ts, val, offsets = make_irregular(5, 40, with_nan=False)
