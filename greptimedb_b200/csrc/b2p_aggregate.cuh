@@ -29,6 +29,8 @@ struct GroupArgs {
   double* out_val;
   uint32_t* out_cnt;
   int32_t accumulate;  // 1: add into existing out_val/out_cnt (SUM/COUNT partial chaining)
+  double* out_mean;    // stddev / stdvar only, may be NULL: when given, out_val receives the raw M2 and out_mean the
+                       // mean — the (count, mean, M2) state another rank's partial can be merged with
 };
 
 // AGG is a compile-time constant so that the per-member fold is one or two instructions (sum / avg / count) instead
@@ -109,6 +111,14 @@ __global__ void __launch_bounds__(256) group_aggregate_kernel(const GroupArgs a)
       a.out_cnt[o] += cnt;
       continue;
     }
+    if constexpr (AGG == B2P_AGG_STDVAR || AGG == B2P_AGG_STDDEV) {
+      if (a.out_mean) {
+        a.out_val[o] = cnt ? m2 : 0.0;
+        a.out_mean[o] = cnt ? mean : 0.0;
+        a.out_cnt[o] = cnt;
+        continue;
+      }
+    }
     double r = 0.0;
     if (cnt > 0) {
       if constexpr (AGG == B2P_AGG_SUM || AGG == B2P_AGG_MIN || AGG == B2P_AGG_MAX) r = acc;
@@ -128,6 +138,34 @@ __global__ void __launch_bounds__(256) group_finalize_kernel(int32_t agg, double
     if (c == 0) { val[i] = 0.0; continue; }
     if (agg == B2P_AGG_AVG) val[i] = val[i] / (double)c;
     else if (agg == B2P_AGG_COUNT) val[i] = (double)c;
+    else if (agg == B2P_AGG_STDVAR) val[i] = val[i] / (double)c;        // merged M2 -> population variance
+    else if (agg == B2P_AGG_STDDEV) val[i] = sqrt(val[i] / (double)c);
+  }
+}
+
+// Cross-rank merge helpers of the by-label partials (b2p_allreduce_partials_dev).
+// phase 0: groups this rank has no row for become the neutral element of min / max; phase 1 (after the all-reduce,
+// cnt = global count): groups absent everywhere read 0.0 again, like a freshly built partial.
+__global__ void __launch_bounds__(256) minmax_neutral_kernel(bool is_min, double* val, const uint32_t* cnt, uint64_t n, int phase) {
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    if (cnt[i] == 0) val[i] = phase == 0 ? (is_min ? inf : -inf) : 0.0;
+}
+// (cnt, mean, M2) states of population variance.  phase 0: wsum = cnt * mean, cnt_r = cnt (kept: cnt becomes global);
+// phase 1 (wsum, cnt all-reduced): mean_g = wsum / cnt; M2 += cnt_r * (mean_r - mean_g)^2 — the all-reduce of M2 that
+// follows yields the merged M2; mean = mean_g.
+__global__ void __launch_bounds__(256) variance_merge_kernel(int phase, double* m2, const uint32_t* cnt, double* mean,
+                                                             double* wsum, uint32_t* cnt_r, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (phase == 0) {
+      cnt_r[i] = cnt[i];
+      wsum[i] = (double)cnt[i] * mean[i];
+    } else {
+      const double mg = cnt[i] ? wsum[i] / (double)cnt[i] : 0.0;
+      const double d = mean[i] - mg;
+      m2[i] = cnt_r[i] ? m2[i] + (double)cnt_r[i] * d * d : 0.0;
+      mean[i] = mg;
+    }
   }
 }
 

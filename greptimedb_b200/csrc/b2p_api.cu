@@ -3,6 +3,7 @@
 // There is NO CPU fallback anywhere in this file: every entry point either launches the CUDA
 // kernels or returns an error.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -42,6 +43,53 @@ int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(B2P_E_CUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// NCCL, bound at run time: libnccl.so.2 is not a link dependency (single-GPU users never need it), and inside a
+// process that already loaded an NCCL (e.g. the one bundled with torch) dlopen hands back that same library.
+// Only the handful of entry points the by-label all-reduce needs; enum values are NCCL's ABI (nccl.h).
+struct Nccl {
+  typedef struct ncclComm* comm_t;
+  struct unique_id { char internal[128]; };
+  enum { kSum = 0, kMax = 2, kMin = 3 };
+  enum { kUint32 = 3, kUint64 = 5, kFloat64 = 8 };
+  int (*GetUniqueId)(unique_id*) = nullptr;
+  int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
+  int (*CommDestroy)(comm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  void* handle = nullptr;
+  bool load() {
+    if (handle) return true;
+    const char* names[] = {getenv("B2P_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n || !*n) continue;
+      handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) return false;
+    bool ok = true;
+    auto sym = [&](const char* n) { void* p = dlsym(handle, n); ok = ok && p; return p; };
+    GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(sym("ncclGetUniqueId"));
+    CommInitRank = reinterpret_cast<decltype(CommInitRank)>(sym("ncclCommInitRank"));
+    CommDestroy = reinterpret_cast<decltype(CommDestroy)>(sym("ncclCommDestroy"));
+    AllReduce = reinterpret_cast<decltype(AllReduce)>(sym("ncclAllReduce"));
+    GroupStart = reinterpret_cast<decltype(GroupStart)>(sym("ncclGroupStart"));
+    GroupEnd = reinterpret_cast<decltype(GroupEnd)>(sym("ncclGroupEnd"));
+    GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
+    if (!ok) { handle = nullptr; }
+    return ok;
+  }
+};
+Nccl g_nccl;
+
+#define NCCL_TRY(x)                                                                                          \
+  do {                                                                                                       \
+    int r__ = (x);                                                                                           \
+    if (r__ != 0) return fail(B2P_E_CUDA, "%s: %s", #x, g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "NCCL error"); \
+  } while (0)
+
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -77,9 +125,18 @@ constexpr int kBigRing = 1024;        // long-window instantiation of the warp-p
 constexpr int kStatusSlots = 32;      // range calls that may be outstanding between two b2p_sync
 constexpr int kSlowCtas = 148;        // slow-path grid (4 warps per CTA)
 constexpr int kSlowWarps = kSlowCtas * 4;
-constexpr size_t kArenaDefaultRows = 1u << 20;
+constexpr size_t kArenaDefaultRows = 1u << 21;  // 32 MB: regions of 3 542 rows for the 592 slow-path warps
 
 }  // namespace
+
+// group -> member-series CSR of one gid[] assignment (b2p_group_index_create_dev), reusable across calls
+struct b2p_group_index {
+  uint32_t n_series = 0, n_groups = 0;
+  uint32_t max_members = 0;      // size of the largest group
+  uint32_t* gid = nullptr;       // [n_series] device copy
+  uint32_t* goff = nullptr;      // [n_groups + 1]
+  uint32_t* members = nullptr;   // [n_series] series ids ordered by (group, series id)
+};
 
 struct b2p_ctx {
   int device = 0;
@@ -95,9 +152,19 @@ struct b2p_ctx {
   int next_slot = 0;
   struct Pending {
     int slot; int fn; RangeArgs args; int lean_mode; bool thread_tier; bool used_lean; uint32_t n_series; bool verdict_taken;
+    bool fused;  // by-label partials were added in place: only the slow kernel may be repeated
+    bool merged; // ... and already all-reduced (or tiled): nothing can be repeated, an arena overflow is an error
   };
   std::vector<Pending> pending;
   DevBuf slow_list, w_list, b_list, arena_ts, arena_val, win_scratch;
+  // multi-GPU (one process per GPU): communicator of the by-label all-reduce, its stream and join event
+  Nccl::comm_t comm = nullptr;
+  int comm_ranks = 1, comm_rank = 0;
+  cudaStream_t s_comm = nullptr;
+  cudaEvent_t ev_comm_in = nullptr, ev_comm_done = nullptr;
+  DevBuf m_tmp0, m_tmp1;             // scratch of the variance merge
+  DevBuf w_skip, b_skip, slow_skip;  // fused by-label partials: steps already added, parallel to the work lists
+  bool fused_pending = false;        // a fused call is outstanding: its work lists must survive until b2p_sync
   // K2T (thread per series) in front of K2 for rate/increase/delta.  Measured slower than K2 on B200
   // (28 vs 64 G samples/s, profiles/r1_thread_tier.md), so it is opt-in: B2P_ENABLE_THREAD_TIER=1.
   bool thread_tier = false;
@@ -117,8 +184,9 @@ struct b2p_ctx {
   uint32_t last_range_series = 0;
   int lean_blocks_per_sm[B2P_FN__COUNT][2] = {};
   size_t arena_rows = 0;
-  cudaEvent_t ev[4][2] = {};
-  bool ev_used[4] = {false, false, false, false};
+  size_t arena_rows_wanted = 0;  // B2P_ARENA_ROWS: initial size of the slow-path arena (default kArenaDefaultRows)
+  cudaEvent_t ev[5][2] = {};  // 0 K0, 1 range tiers, 2 slow kernel, 3 by-label aggregate, 4 all-reduce (last tile)
+  bool ev_used[5] = {false, false, false, false, false};
   long long launches = 0;
   long long last_slow = 0;
   long long last_w = 0;
@@ -157,6 +225,11 @@ void stage_begin(b2p_ctx* c, int stage) {
 }
 void stage_end(b2p_ctx* c, int stage) {
   cudaEventRecord(c->ev[stage][1], c->stream);
+  c->ev_used[stage] = true;
+}
+void stage_begin_on(b2p_ctx* c, int stage, cudaStream_t s) { cudaEventRecord(c->ev[stage][0], s); }
+void stage_end_on(b2p_ctx* c, int stage, cudaStream_t s) {
+  cudaEventRecord(c->ev[stage][1], s);
   c->ev_used[stage] = true;
 }
 
@@ -282,6 +355,40 @@ int launch_lean_if_supported(b2p_ctx* c, const RangeArgs& a, bool with_flags) {
   }
 }
 
+// First tier of the fused by-label SUM: rate / increase / delta walk the series group by group and add into
+// gsum / gcnt (range_lean_kernel<FN, FLAGS, GROUPED = true>).
+template <int FN, bool FLAGS>
+int launch_lean_grouped(b2p_ctx* c, const RangeArgs& a) {
+  constexpr size_t smem = lean_smem_bytes();
+  auto kern = range_lean_kernel<FN, FLAGS, true>;
+  static int cached_nb[16] = {};  // per device
+  int& cached = cached_nb[c->device & 15];
+  if (cached == 0) {
+    int nb = 0;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarpsPerCta * 32, smem));
+    cached = nb > 0 ? nb : 1;
+  }
+  const unsigned n_g = a.g_hi - a.g_lo;
+  const unsigned need = (n_g + kWarpsPerCta - 1) / kWarpsPerCta;
+  const unsigned cap = (unsigned)(c->num_sms * cached);
+  const unsigned grid = need < cap ? need : cap;
+  if (grid == 0) return B2P_OK;
+  kern<<<grid, kWarpsPerCta * 32, smem, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+bool lean_grouped_fn(int fn) { return fn == B2P_FN_RATE || fn == B2P_FN_INCREASE || fn == B2P_FN_DELTA; }
+int dispatch_lean_grouped(b2p_ctx* c, int fn, const RangeArgs& a, bool with_flags) {
+  switch (fn) {
+    case B2P_FN_RATE: return with_flags ? launch_lean_grouped<B2P_FN_RATE, true>(c, a) : launch_lean_grouped<B2P_FN_RATE, false>(c, a);
+    case B2P_FN_INCREASE: return with_flags ? launch_lean_grouped<B2P_FN_INCREASE, true>(c, a) : launch_lean_grouped<B2P_FN_INCREASE, false>(c, a);
+    case B2P_FN_DELTA: return launch_lean_grouped<B2P_FN_DELTA, false>(c, a);
+  }
+  return fail(B2P_E_INVALID, "fn_id %d has no fused by-label tier", fn);
+}
+
 int dispatch_lean(b2p_ctx* c, int fn, const RangeArgs& a, bool with_flags) {
   switch (fn) {
 #define X(N) case N: return launch_lean_if_supported<N>(c, a, with_flags);
@@ -385,9 +492,10 @@ int ensure_slow_scratch(b2p_ctx* c, uint32_t n_series, int64_t T) {
   if ((rc = c->b_list.ensure((size_t)(n_series ? n_series : 1) * 4))) return rc;
   if ((rc = c->win_scratch.ensure((size_t)kSlowWarps * (size_t)(T > 0 ? T : 1) * 8))) return rc;
   if (c->arena_rows == 0) {
-    if ((rc = c->arena_ts.ensure(kArenaDefaultRows * 8))) return rc;
-    if ((rc = c->arena_val.ensure(kArenaDefaultRows * 8))) return rc;
-    c->arena_rows = kArenaDefaultRows;
+    const size_t rows = c->arena_rows_wanted > kArenaDefaultRows ? c->arena_rows_wanted : kArenaDefaultRows;
+    if ((rc = c->arena_ts.ensure(rows * 8))) return rc;
+    if ((rc = c->arena_val.ensure(rows * 8))) return rc;
+    c->arena_rows = rows;
   }
   return B2P_OK;
 }
@@ -431,7 +539,7 @@ b2p_ctx* b2p_create(int device) {
   ok = ok && cudaMallocHost(&c->h_ring, kStatusSlots * sizeof(Status)) == cudaSuccess;
   ok = ok && cudaMalloc(&c->d_k0, sizeof(Status)) == cudaSuccess;
   ok = ok && cudaMallocHost(&c->h_k0, sizeof(Status)) == cudaSuccess;
-  for (int i = 0; ok && i < 4; ++i)
+  for (int i = 0; ok && i < 5; ++i)
     for (int j = 0; j < 2; ++j) ok = ok && cudaEventCreate(&c->ev[i][j]) == cudaSuccess;
   if (!ok) {
     fail(B2P_E_CUDA, "context creation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -454,6 +562,7 @@ b2p_ctx* b2p_create(int device) {
   if (const char* e = getenv("B2P_DISABLE_LEAN_TIER")) c->lean_tier = !(e[0] == '1');
   if (const char* e = getenv("B2P_LEAN_ADAPTIVE")) c->lean_adaptive = !(e[0] == '0');
   if (const char* e = getenv("B2P_LEAN_FORCE_FLAGS")) c->lean_force_flags = (e[0] == '1');
+  if (const char* e = getenv("B2P_ARENA_ROWS")) c->arena_rows_wanted = (size_t)strtoull(e, nullptr, 10);
   return c;
 }
 
@@ -461,12 +570,17 @@ void b2p_destroy(b2p_ctx* c) {
   if (!c) return;
   DeviceGuard g(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  if (c->s_comm) cudaStreamDestroy(c->s_comm);
+  if (c->ev_comm_in) cudaEventDestroy(c->ev_comm_in);
+  if (c->ev_comm_done) cudaEventDestroy(c->ev_comm_done);
+  for (DevBuf* b : {&c->w_skip, &c->b_skip, &c->slow_skip, &c->m_tmp0, &c->m_tmp1}) b->release();
   for (DevBuf* b : {&c->slow_list, &c->w_list, &c->b_list, &c->arena_ts, &c->arena_val, &c->win_scratch, &c->h_ts, &c->h_val, &c->h_sid,
                     &c->h_off, &c->h_out, &c->h_valid, &c->h_aux0, &c->h_aux1, &c->h_aux2, &c->h_aux3,
                     &c->g_keys_in, &c->g_keys_out, &c->g_vals_in, &c->g_vals_out, &c->g_goff, &c->g_tmp, &c->c_psum,
                     &c->c_pcnt})
     b->release();
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 5; ++i)
     for (int j = 0; j < 2; ++j)
       if (c->ev[i][j]) cudaEventDestroy(c->ev[i][j]);
   for (int i = 0; i < 2; ++i) {
@@ -503,7 +617,7 @@ int64_t b2p_last_warp_tier_series(b2p_ctx* c) { return c ? c->last_w : -1; }
 int64_t b2p_launch_count(b2p_ctx* c) { return c ? c->launches : -1; }
 
 double b2p_last_kernel_ms(b2p_ctx* c, int stage) {
-  if (!c || stage < 0 || stage >= 4 || !c->ev_used[stage]) return -1.0;
+  if (!c || stage < 0 || stage >= 5 || !c->ev_used[stage]) return -1.0;
   DeviceGuard g(c->device);
   float ms = -1.f;
   if (cudaEventElapsedTime(&ms, c->ev[stage][0], c->ev[stage][1]) != cudaSuccess) {
@@ -515,9 +629,15 @@ double b2p_last_kernel_ms(b2p_ctx* c, int stage) {
 
 // Launches every tier of one range call (first tier when `used_lean`/`thread_tier`, warp-per-series kernel, its
 // long-window instantiation, exact slow kernel) on the context's stream.
-static int launch_range_tiers(b2p_ctx* c, int fn, RangeArgs a, bool thread_tier, bool used_lean, int lean_mode) {
+static int launch_range_tiers(b2p_ctx* c, int fn, RangeArgs a, bool thread_tier, bool used_lean, int lean_mode,
+                              bool later_tile = false) {
   int rc;
-  CU(cudaMemsetAsync(a.status, 0, sizeof(Status), c->stream));
+  if (!later_tile) {
+    CU(cudaMemsetAsync(a.status, 0, sizeof(Status), c->stream));
+  } else {  // a further tile of the same fused call: new work lists, same verdict (overflow / arena fields stay)
+    CU(cudaMemsetAsync(&a.status->slow_count, 0, sizeof(uint32_t), c->stream));
+    CU(cudaMemsetAsync(&a.status->w_count, 0, 2 * sizeof(uint32_t), c->stream));
+  }
   stage_begin(c, 1);
   if (thread_tier) {
     if (fn == B2P_FN_RATE) rc = launch_thread_tier<B2P_FN_RATE>(c, a);
@@ -526,7 +646,7 @@ static int launch_range_tiers(b2p_ctx* c, int fn, RangeArgs a, bool thread_tier,
     if (rc) return rc;
     a.use_w_list = 1;
   } else if (used_lean) {
-    if ((rc = dispatch_lean(c, fn, a, lean_mode == 1))) return rc;
+    if ((rc = a.gsum ? dispatch_lean_grouped(c, fn, a, lean_mode == 1) : dispatch_lean(c, fn, a, lean_mode == 1))) return rc;
     a.use_w_list = 1;
   }
   rc = dispatch_fast(c, fn, a);
@@ -572,6 +692,7 @@ int b2p_sync(b2p_ctx* c) {
       }
     }
     c->pending.clear();
+    c->fused_pending = false;
     if (redo.empty()) return B2P_OK;
     int rc;
     if ((rc = c->arena_ts.ensure(need * 8))) return rc;
@@ -581,6 +702,22 @@ int b2p_sync(b2p_ctx* c) {
       pc.args.arena_ts = c->arena_ts.as<int64_t>();
       pc.args.arena_val = c->arena_val.as<double>();
       pc.args.arena_cap = need;
+      if (pc.merged)
+        return fail(B2P_E_TOO_LARGE, "a series of %llu+ rows needs the exact slow path but does not fit its arena region; "
+                    "the merged partials are incomplete — set B2P_ARENA_ROWS >= %zu and repeat the query",
+                    (unsigned long long)(need / (size_t)kSlowWarps), need);
+      if (pc.fused) {
+        // partials were added in place: only the slow kernel runs again, over its intact work list (a series that
+        // did not fit the arena added nothing); no other range call was admitted while this one was outstanding
+        Status patch = c->h_ring[pc.slot];
+        patch.arena_overflow = 0; patch.arena_used = 0; patch.arena_needed = 0;
+        c->h_ring[pc.slot] = patch;
+        CU(cudaMemcpyAsync(c->d_ring + pc.slot, c->h_ring + pc.slot, sizeof(Status), cudaMemcpyHostToDevice, c->stream));
+        if ((rc = dispatch_slow(c, pc.fn, pc.args))) return rc;
+        c->pending.push_back(pc);
+        CU(cudaStreamSynchronize(c->stream));
+        continue;
+      }
       if ((rc = launch_range_tiers(c, pc.fn, pc.args, pc.thread_tier, pc.used_lean, pc.lean_mode))) return rc;
       c->pending.push_back(pc);
       CU(cudaStreamSynchronize(c->stream));  // one redone call at a time: they share the arena from offset 0
@@ -615,15 +752,60 @@ static int series_offsets_impl(b2p_ctx* c, const uint32_t* sid, uint64_t n_rows,
   return B2P_OK;
 }
 
+// Target of a fused by-label SUM / COUNT (b2p_range_group_sum*_dev): groups [g_lo, g_hi) of an index.
+struct GroupTarget {
+  const b2p_group_index* idx;
+  uint32_t g_lo, g_hi;
+  double* gsum;
+  uint32_t* gcnt;
+  // > 0: the group range is processed in this many tiles and every tile's rows of gsum / gcnt are all-reduced over
+  // the context's communicator as soon as the tile is complete, on the (high-priority) communication stream, while
+  // the next tile computes
+  int allreduce_tiles;
+};
+
+// Can this range call add its results straight into by-label partials?  (first tier available for the function and
+// the query shape, and not switched off by the adaptive policy; groups balanced enough for group-exclusive warps)
+static bool fused_group_ok(b2p_ctx* c, const b2p_range_params* p, int64_t T, const b2p_group_index* idx) {
+  if (!lean_grouped_fn(p->fn_id) || c->thread_tier) return false;
+  RangeArgs a{};
+  a.start = p->start; a.end = p->end; a.interval = p->interval; a.range = p->range;
+  a.T = T;
+  a.rcp_rs = 1.0;
+  if (fits_ts32(a)) a.rel_max = (uint32_t)(p->range + (T - 1) * p->interval + 1);
+  {
+    const double rs = (double)p->range / 1000.0;
+    uint64_t bits;
+    memcpy(&bits, &rs, 8);
+    if (p->range <= 0 || (bits & 0x000fffffffffffffull) == 0x000fffffffffffffull) a.rcp_rs = 0.0;
+  }
+  if (!lean_ok(c, p->fn_id, a)) return false;
+  if (c->lean_backoff[p->fn_id] > 0 && c->lean_mode[p->fn_id] == 2) return false;
+  // a group is walked by ONE warp: the largest group may not exceed a few times a warp's fair share
+  const uint64_t warps = (uint64_t)c->num_sms * 3 * kWarpsPerCta;
+  const uint64_t share = idx->n_series / warps + 1;
+  return (uint64_t)idx->max_members <= 8 * share + 64;
+}
+
+static int range_call(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val,
+                      const uint64_t* offsets, uint64_t n_rows, uint32_t n_series, double* out, uint32_t* valid_words,
+                      const GroupTarget* gt);
+
 int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val,
                        const uint64_t* offsets, uint64_t n_rows, uint32_t n_series, double* out,
                        uint32_t* valid_words) {
+  return range_call(c, p, ts, val, offsets, n_rows, n_series, out, valid_words, nullptr);
+}
+
+static int range_call(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val,
+                      const uint64_t* offsets, uint64_t n_rows, uint32_t n_series, double* out, uint32_t* valid_words,
+                      const GroupTarget* gt) {
   if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
   int64_t T = 0;
   int rc = check_grid(p, n_series, &T);
   if (rc) return rc;
   if (n_series == 0 || T == 0) return B2P_OK;
-  if (!offsets || !out || !valid_words || ((!ts || !val) && n_rows)) return fail(B2P_E_INVALID, "NULL argument");
+  if (!offsets || (!gt && (!out || !valid_words)) || ((!ts || !val) && n_rows)) return fail(B2P_E_INVALID, "NULL argument");
   if (!aligned16(ts) || !aligned16(val)) return fail(B2P_E_INVALID, "ts/val must be 16-byte aligned");
   DeviceGuard g(c->device);
   if ((rc = ensure_slow_scratch(c, n_series, T))) return rc;
@@ -647,6 +829,16 @@ int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts,
   }
   a.ts = ts; a.val = val; a.offsets = offsets; a.n_rows = n_rows; a.n_series = n_series;
   a.out = out; a.valid = valid_words;
+  // a fused call keeps the work lists until its verdict is in: nothing else is admitted before that
+  if (c->fused_pending && (rc = b2p_sync(c))) return rc;
+  if (gt) {
+    if (!c->pending.empty() && (rc = b2p_sync(c))) return rc;
+    const size_t ns = n_series;
+    if ((rc = c->w_skip.ensure(ns * 4)) || (rc = c->b_skip.ensure(ns * 4)) || (rc = c->slow_skip.ensure(ns * 4))) return rc;
+    a.gsum = gt->gsum; a.gcnt = gt->gcnt; a.gid = gt->idx->gid; a.g_off = gt->idx->goff; a.g_members = gt->idx->members;
+    a.n_groups = gt->idx->n_groups; a.g_lo = gt->g_lo; a.g_hi = gt->g_hi;
+    a.w_skip = c->w_skip.as<uint32_t>(); a.b_skip = c->b_skip.as<uint32_t>(); a.slow_skip = c->slow_skip.as<uint32_t>();
+  }
   // every call owns a status slot until b2p_sync has read it; with all slots taken the library synchronises itself
   if ((int)c->pending.size() >= kStatusSlots && (rc = b2p_sync(c))) return rc;
   const int slot = c->next_slot;
@@ -672,15 +864,46 @@ int b2p_range_eval_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts,
     if (mode != 2) used_lean = true;
     if (mode == 0 && c->lean_force_flags) mode = 1;
   }
+  if (gt && !used_lean) return fail(B2P_E_INVALID, "fused by-label call without its first tier (internal)");
   c->last_lean_mode = mode;
   c->last_used_lean = used_lean;
   c->last_range_series = n_series;
   c->last_range_fn = p->fn_id;
-  if ((rc = launch_range_tiers(c, p->fn_id, a, tier1, used_lean, mode))) return rc;
+  if (gt && gt->allreduce_tiles > 0) {
+    if (!c->comm && c->comm_ranks > 1) return fail(B2P_E_INVALID, "no communicator: call b2p_comm_init first");
+    const uint32_t n_t = (uint32_t)gt->allreduce_tiles;
+    const uint64_t span = (uint64_t)gt->g_hi - gt->g_lo;
+    for (uint32_t t = 0; t < n_t; ++t) {
+      a.g_lo = gt->g_lo + (uint32_t)(span * t / n_t);
+      a.g_hi = gt->g_lo + (uint32_t)(span * (t + 1) / n_t);
+      if (a.g_hi == a.g_lo) continue;
+      if ((rc = launch_range_tiers(c, p->fn_id, a, tier1, used_lean, mode, t > 0))) return rc;
+      if (c->comm) {
+        const size_t off = (size_t)a.g_lo * (size_t)T, cnt_n = (size_t)(a.g_hi - a.g_lo) * (size_t)T;
+        CU(cudaEventRecord(c->ev_comm_in, c->stream));
+        CU(cudaStreamWaitEvent(c->s_comm, c->ev_comm_in, 0));
+        stage_begin_on(c, 4, c->s_comm);
+        NCCL_TRY(g_nccl.GroupStart());
+        NCCL_TRY(g_nccl.AllReduce(a.gsum + off, a.gsum + off, cnt_n, Nccl::kFloat64, Nccl::kSum, c->comm, c->s_comm));
+        NCCL_TRY(g_nccl.AllReduce(a.gcnt + off, a.gcnt + off, cnt_n, Nccl::kUint32, Nccl::kSum, c->comm, c->s_comm));
+        NCCL_TRY(g_nccl.GroupEnd());
+        stage_end_on(c, 4, c->s_comm);
+      }
+    }
+    if (c->comm) {  // everything after this call on the context's stream sees the merged partials
+      CU(cudaEventRecord(c->ev_comm_done, c->s_comm));
+      CU(cudaStreamWaitEvent(c->stream, c->ev_comm_done, 0));
+    }
+    a.g_lo = gt->g_lo; a.g_hi = gt->g_hi;
+  } else if ((rc = launch_range_tiers(c, p->fn_id, a, tier1, used_lean, mode))) {
+    return rc;
+  }
   b2p_ctx::Pending pc{};
   pc.slot = slot; pc.fn = p->fn_id; pc.args = a; pc.lean_mode = mode; pc.thread_tier = tier1; pc.used_lean = used_lean;
-  pc.n_series = n_series; pc.verdict_taken = false;
+  pc.n_series = n_series; pc.verdict_taken = false; pc.fused = gt != nullptr;
+  pc.merged = gt && gt->allreduce_tiles > 0;
   c->pending.push_back(pc);
+  if (gt) c->fused_pending = true;
   return B2P_OK;
 }
 
@@ -726,52 +949,38 @@ int b2p_instant_select_dev(b2p_ctx* c, int64_t start, int64_t end, int64_t inter
 }
 
 namespace {
-int group_aggregate_impl(b2p_ctx* c, int32_t agg, const double* vals, const uint32_t* valid_words, const uint32_t* gid,
-                         uint32_t n_series, uint32_t n_groups, uint64_t T, double* out_val, uint32_t* out_cnt,
-                         int accumulate);
-}
-
-int b2p_group_aggregate_dev(b2p_ctx* c, int32_t agg, const double* vals, const uint32_t* valid_words,
-                            const uint32_t* gid, uint32_t n_series, uint32_t n_groups, uint64_t T, double* out_val,
-                            uint32_t* out_cnt) {
-  return group_aggregate_impl(c, agg, vals, valid_words, gid, n_series, n_groups, T, out_val, out_cnt, 0);
-}
-
-namespace {
-// accumulate = 1 (SUM / COUNT partials only): out_val / out_cnt are added to instead of overwritten
-int group_aggregate_impl(b2p_ctx* c, int32_t agg, const double* vals, const uint32_t* valid_words, const uint32_t* gid,
-                         uint32_t n_series, uint32_t n_groups, uint64_t T, double* out_val, uint32_t* out_cnt,
-                         int accumulate) {
-  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
-  if (agg < 0 || agg > B2P_AGG_STDVAR) return fail(B2P_E_INVALID, "unknown aggregator %d", agg);
-  if (n_groups == 0 || T == 0) return B2P_OK;
-  if (!vals || !valid_words || !gid || !out_val || !out_cnt) return fail(B2P_E_INVALID, "NULL argument");
-  DeviceGuard g(c->device);
+// group -> member series CSR: stable radix sort of (gid, series index), then lower bounds per group
+int build_group_csr(b2p_ctx* c, const uint32_t* gid, uint32_t n_series, uint32_t n_groups, uint32_t* goff,
+                    uint32_t* members) {
   int rc;
   const size_t ns = n_series ? n_series : 1;
   if ((rc = c->g_vals_in.ensure(ns * 4))) return rc;
-  if ((rc = c->g_vals_out.ensure(ns * 4))) return rc;
   if ((rc = c->g_keys_out.ensure(ns * 4))) return rc;
-  if ((rc = c->g_goff.ensure(((size_t)n_groups + 1) * 4))) return rc;
-  stage_begin(c, 3);
-  // group -> member series CSR: stable radix sort of (gid, series index)
   iota_kernel<<<(unsigned)((ns + 255) / 256 < 1024 ? (ns + 255) / 256 : 1024), 256, 0, c->stream>>>(
       c->g_vals_in.as<uint32_t>(), n_series);
   c->launches++;
   size_t tmp_bytes = 0;
   CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, gid, c->g_keys_out.as<uint32_t>(), c->g_vals_in.as<uint32_t>(),
-                                     c->g_vals_out.as<uint32_t>(), (int)n_series, 0, 32, c->stream));
+                                     members, (int)n_series, 0, 32, c->stream));
   if ((rc = c->g_tmp.ensure(tmp_bytes ? tmp_bytes : 16))) return rc;
   if (n_series > 0)
     CU(cub::DeviceRadixSort::SortPairs(c->g_tmp.p, tmp_bytes, gid, c->g_keys_out.as<uint32_t>(),
-                                       c->g_vals_in.as<uint32_t>(), c->g_vals_out.as<uint32_t>(), (int)n_series, 0, 32,
-                                       c->stream));
+                                       c->g_vals_in.as<uint32_t>(), members, (int)n_series, 0, 32, c->stream));
   group_offsets_kernel<<<(n_groups + 1 + 255) / 256, 256, 0, c->stream>>>(c->g_keys_out.as<uint32_t>(), n_series,
-                                                                          n_groups, c->g_goff.as<uint32_t>());
+                                                                          n_groups, goff);
   c->launches++;
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+// accumulate = 1 (SUM / COUNT partials only): out_val / out_cnt are added to instead of overwritten
+int group_aggregate_csr(b2p_ctx* c, int32_t agg, const double* vals, const uint32_t* valid_words, const uint32_t* goff,
+                        const uint32_t* members, uint32_t n_groups, uint64_t T, double* out_val, uint32_t* out_cnt,
+                        int accumulate, double* out_mean = nullptr) {
   GroupArgs a{};
-  a.agg = agg; a.vals = vals; a.valid = valid_words; a.goff = c->g_goff.as<uint32_t>();
-  a.members = c->g_vals_out.as<uint32_t>(); a.n_groups = n_groups; a.T = T; a.Tw = (uint32_t)((T + 31) / 32);
+  a.out_mean = out_mean;
+  a.agg = agg; a.vals = vals; a.valid = valid_words; a.goff = goff;
+  a.members = members; a.n_groups = n_groups; a.T = T; a.Tw = (uint32_t)((T + 31) / 32);
   a.out_val = out_val; a.out_cnt = out_cnt; a.accumulate = accumulate;
   const uint64_t warps = (uint64_t)n_groups * ((T + 31) / 32);
   uint64_t blocks = (warps + 7) / 8;
@@ -787,22 +996,126 @@ int group_aggregate_impl(b2p_ctx* c, int32_t agg, const double* vals, const uint
     default: group_aggregate_kernel<B2P_AGG_STDDEV><<<(unsigned)blocks, 256, 0, c->stream>>>(a); break;
   }
   c->launches++;
-  stage_end(c, 3);
   CU(cudaGetLastError());
   return B2P_OK;
 }
+
+int group_aggregate_impl(b2p_ctx* c, int32_t agg, const double* vals, const uint32_t* valid_words, const uint32_t* gid,
+                         uint32_t n_series, uint32_t n_groups, uint64_t T, double* out_val, uint32_t* out_cnt,
+                         int accumulate, double* out_mean = nullptr) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (agg < 0 || agg > B2P_AGG_STDVAR) return fail(B2P_E_INVALID, "unknown aggregator %d", agg);
+  if (n_groups == 0 || T == 0) return B2P_OK;
+  if (!vals || !valid_words || !gid || !out_val || !out_cnt) return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  int rc;
+  const size_t ns = n_series ? n_series : 1;
+  if ((rc = c->g_vals_out.ensure(ns * 4))) return rc;
+  if ((rc = c->g_goff.ensure(((size_t)n_groups + 1) * 4))) return rc;
+  stage_begin(c, 3);
+  if ((rc = build_group_csr(c, gid, n_series, n_groups, c->g_goff.as<uint32_t>(), c->g_vals_out.as<uint32_t>()))) return rc;
+  rc = group_aggregate_csr(c, agg, vals, valid_words, c->g_goff.as<uint32_t>(), c->g_vals_out.as<uint32_t>(), n_groups, T,
+                           out_val, out_cnt, accumulate, out_mean);
+  stage_end(c, 3);
+  return rc;
+}
 }  // namespace
 
-int b2p_range_group_sum_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val,
-                            const uint64_t* offsets, uint64_t n_rows, uint32_t n_series, const uint32_t* gid,
-                            uint32_t n_groups, double* out_sum, uint32_t* out_cnt) {
-  // Composition for now: range function into context scratch, then by-label partial SUM/COUNT.
-  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+int b2p_group_aggregate_dev(b2p_ctx* c, int32_t agg, const double* vals, const uint32_t* valid_words,
+                            const uint32_t* gid, uint32_t n_series, uint32_t n_groups, uint64_t T, double* out_val,
+                            uint32_t* out_cnt) {
+  return group_aggregate_impl(c, agg, vals, valid_words, gid, n_series, n_groups, T, out_val, out_cnt, 0);
+}
+
+int b2p_group_aggregate_partial_dev(b2p_ctx* c, int32_t agg, const double* vals, const uint32_t* valid_words,
+                                    const uint32_t* gid, uint32_t n_series, uint32_t n_groups, uint64_t T,
+                                    double* out_val, uint32_t* out_cnt, double* out_mean) {
+  const bool var = agg == B2P_AGG_STDDEV || agg == B2P_AGG_STDVAR;
+  if (var && !out_mean) return fail(B2P_E_INVALID, "stddev / stdvar partials need out_mean");
+  if (agg == B2P_AGG_AVG) agg = B2P_AGG_SUM;  // the partial of an average is (sum, count)
+  return group_aggregate_impl(c, agg, vals, valid_words, gid, n_series, n_groups, T, out_val, out_cnt, 0,
+                              var ? out_mean : nullptr);
+}
+
+int b2p_group_index_create_dev(b2p_ctx* c, const uint32_t* gid, uint32_t n_series, uint32_t n_groups,
+                               b2p_group_index** out_index) {
+  if (!c || !out_index || (!gid && n_series)) return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  b2p_group_index* ix = new (std::nothrow) b2p_group_index();
+  if (!ix) return fail(B2P_E_NOMEM, "out of host memory");
+  ix->n_series = n_series; ix->n_groups = n_groups;
+  const size_t ns = n_series ? n_series : 1;
+  bool ok = cudaMalloc(&ix->gid, ns * 4) == cudaSuccess && cudaMalloc(&ix->members, ns * 4) == cudaSuccess &&
+            cudaMalloc(&ix->goff, ((size_t)n_groups + 1) * 4) == cudaSuccess;
+  int rc = ok ? B2P_OK : fail(B2P_E_NOMEM, "cudaMalloc failed for the group index");
+  if (!rc && n_series) {
+    cudaMemcpyAsync(ix->gid, gid, (size_t)n_series * 4, cudaMemcpyDeviceToDevice, c->stream);
+    rc = build_group_csr(c, ix->gid, n_series, n_groups, ix->goff, ix->members);
+  }
+  if (!rc) {
+    // largest group (host-side scan of the offsets: the index is built once per label assignment)
+    std::vector<uint32_t> h((size_t)n_groups + 1);
+    cudaError_t e = cudaMemcpyAsync(h.data(), ix->goff, h.size() * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = fail(B2P_E_CUDA, "group index read-back: %s", cudaGetErrorString(e));
+    for (uint32_t i = 0; !rc && i < n_groups; ++i)
+      if (h[i + 1] - h[i] > ix->max_members) ix->max_members = h[i + 1] - h[i];
+  }
+  if (rc) {
+    b2p_group_index_destroy(c, ix);
+    return rc;
+  }
+  *out_index = ix;
+  return B2P_OK;
+}
+
+void b2p_group_index_destroy(b2p_ctx* c, b2p_group_index* ix) {
+  if (!ix) return;
+  if (c) {
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (ix->gid) cudaFree(ix->gid);
+    if (ix->goff) cudaFree(ix->goff);
+    if (ix->members) cudaFree(ix->members);
+  }
+  delete ix;
+}
+
+int b2p_group_aggregate_indexed_dev(b2p_ctx* c, int32_t agg, const double* vals, const uint32_t* valid_words,
+                                    const b2p_group_index* ix, uint64_t T, double* out_val, uint32_t* out_cnt) {
+  if (!c || !ix) return fail(B2P_E_INVALID, "NULL argument");
+  if (agg < 0 || agg > B2P_AGG_STDVAR) return fail(B2P_E_INVALID, "unknown aggregator %d", agg);
+  if (ix->n_groups == 0 || T == 0) return B2P_OK;
+  if (!vals || !valid_words || !out_val || !out_cnt) return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  stage_begin(c, 3);
+  int rc = group_aggregate_csr(c, agg, vals, valid_words, ix->goff, ix->members, ix->n_groups, T, out_val, out_cnt, 0);
+  stage_end(c, 3);
+  return rc;
+}
+
+// sum by (..)(fn(..)) partials of groups [g_lo, g_hi) added into out_sum / out_cnt [n_groups x T].
+// Fused (no [n_series x T] intermediate) for rate / increase / delta whenever the first tier applies; otherwise the
+// range function is evaluated into context scratch and folded by the by-label kernel (two passes, synchronous).
+int b2p_range_group_sum_indexed_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val,
+                                    const uint64_t* offsets, uint64_t n_rows, uint32_t n_series,
+                                    const b2p_group_index* ix, uint32_t g_lo, uint32_t g_hi, double* out_sum,
+                                    uint32_t* out_cnt) {
+  if (!c || !ix) return fail(B2P_E_INVALID, "NULL argument");
+  if (ix->n_series != n_series) return fail(B2P_E_INVALID, "group index was built for %u series, call has %u", ix->n_series, n_series);
+  if (g_hi > ix->n_groups) g_hi = ix->n_groups;
   int64_t T = 0;
   int rc = check_grid(p, n_series, &T);
   if (rc) return rc;
-  if (n_series == 0 || T == 0 || n_groups == 0) return B2P_OK;
+  if (n_series == 0 || T == 0 || g_lo >= g_hi) return B2P_OK;
+  if (!out_sum || !out_cnt) return fail(B2P_E_INVALID, "NULL argument");
   DeviceGuard g(c->device);
+  if (fused_group_ok(c, p, T, ix)) {
+    GroupTarget gt{ix, g_lo, g_hi, out_sum, out_cnt, 0};
+    return range_call(c, p, ts, val, offsets, n_rows, n_series, nullptr, nullptr, &gt);
+  }
+  if (g_lo != 0 || g_hi != ix->n_groups)
+    return fail(B2P_E_INVALID, "group ranges need the fused tier (rate / increase / delta in the 32-bit time domain)");
   const uint32_t Tw = (uint32_t)((T + 31) / 32);
   if ((rc = c->h_aux0.ensure((size_t)n_series * (size_t)T * 8))) return rc;
   if ((rc = c->h_aux1.ensure((size_t)n_series * Tw * 4))) return rc;
@@ -810,9 +1123,150 @@ int b2p_range_group_sum_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t
                                c->h_aux1.as<uint32_t>())))
     return rc;
   if ((rc = b2p_sync(c))) return rc;  // slow-path fix-ups must land before the aggregate reads
-  // by-label partials added straight into the caller's buffers (K3 in accumulate mode)
-  return group_aggregate_impl(c, B2P_AGG_SUM, c->h_aux0.as<double>(), c->h_aux1.as<uint32_t>(), gid, n_series, n_groups,
-                              (uint64_t)T, out_sum, out_cnt, 1);
+  stage_begin(c, 3);
+  rc = group_aggregate_csr(c, B2P_AGG_SUM, c->h_aux0.as<double>(), c->h_aux1.as<uint32_t>(), ix->goff, ix->members,
+                           ix->n_groups, (uint64_t)T, out_sum, out_cnt, 1);
+  stage_end(c, 3);
+  return rc;
+}
+
+// sum by over all ranks: the fused partials of this rank's series, tile by tile, each tile all-reduced over the
+// communicator while the next one computes.  Falls back to partials + one all-reduce when the call cannot run fused.
+int b2p_range_group_sum_allreduce_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val,
+                                      const uint64_t* offsets, uint64_t n_rows, uint32_t n_series,
+                                      const b2p_group_index* ix, int32_t n_tiles, double* out_sum, uint32_t* out_cnt) {
+  if (!c || !ix) return fail(B2P_E_INVALID, "NULL argument");
+  if (ix->n_series != n_series) return fail(B2P_E_INVALID, "group index was built for %u series, call has %u", ix->n_series, n_series);
+  int64_t T = 0;
+  int rc = check_grid(p, n_series, &T);
+  if (rc) return rc;
+  if (T == 0 || ix->n_groups == 0) return B2P_OK;
+  if (!out_sum || !out_cnt) return fail(B2P_E_INVALID, "NULL argument");
+  if (n_tiles < 1) n_tiles = 1;
+  DeviceGuard g(c->device);
+  if (n_series > 0 && fused_group_ok(c, p, T, ix)) {
+    GroupTarget gt{ix, 0, ix->n_groups, out_sum, out_cnt, n_tiles};
+    return range_call(c, p, ts, val, offsets, n_rows, n_series, nullptr, nullptr, &gt);
+  }
+  if (n_series > 0 &&
+      (rc = b2p_range_group_sum_indexed_dev(c, p, ts, val, offsets, n_rows, n_series, ix, 0, ix->n_groups, out_sum, out_cnt)))
+    return rc;
+  return b2p_allreduce_partials_dev(c, B2P_AGG_SUM, out_sum, out_cnt, nullptr, (uint64_t)ix->n_groups * (uint64_t)T);
+}
+
+int b2p_range_group_sum_fused(b2p_ctx* c, const b2p_range_params* p, const b2p_group_index* ix) {
+  if (!c || !ix || !p) return 0;
+  int64_t T = b2p_num_steps(p->start, p->end, p->interval);
+  return fused_group_ok(c, p, T, ix) ? 1 : 0;
+}
+
+int b2p_range_group_sum_dev(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val,
+                            const uint64_t* offsets, uint64_t n_rows, uint32_t n_series, const uint32_t* gid,
+                            uint32_t n_groups, double* out_sum, uint32_t* out_cnt) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (n_series == 0 || n_groups == 0) return B2P_OK;
+  b2p_group_index* ix = nullptr;
+  int rc = b2p_group_index_create_dev(c, gid, n_series, n_groups, &ix);
+  if (rc) return rc;
+  rc = b2p_range_group_sum_indexed_dev(c, p, ts, val, offsets, n_rows, n_series, ix, 0, n_groups, out_sum, out_cnt);
+  if (!rc) rc = b2p_sync(c);  // the temporary index must outlive the kernels that read it
+  b2p_group_index_destroy(c, ix);
+  return rc;
+}
+
+/* ---- multi-GPU: all-reduce of by-label partials over NCCL ----------------------------------------- */
+
+int b2p_comm_unique_id(void* out_id, size_t bytes) {
+  if (!out_id || bytes < sizeof(Nccl::unique_id)) return fail(B2P_E_INVALID, "need a %zu-byte buffer", sizeof(Nccl::unique_id));
+  if (!g_nccl.load()) return fail(B2P_E_CUDA, "libnccl.so.2 not found (%s)", dlerror() ? dlerror() : "dlopen");
+  Nccl::unique_id id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  memcpy(out_id, &id, sizeof id);
+  return B2P_OK;
+}
+
+int b2p_comm_init(b2p_ctx* c, const void* id_bytes, size_t bytes, int n_ranks, int rank) {
+  if (!c || !id_bytes || bytes < sizeof(Nccl::unique_id) || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+    return fail(B2P_E_INVALID, "bad communicator arguments");
+  if (c->comm) return fail(B2P_E_INVALID, "context already has a communicator");
+  if (!g_nccl.load()) return fail(B2P_E_CUDA, "libnccl.so.2 not found (%s)", dlerror() ? dlerror() : "dlopen");
+  DeviceGuard g(c->device);
+  Nccl::unique_id id;
+  memcpy(&id, id_bytes, sizeof id);
+  NCCL_TRY(g_nccl.CommInitRank(&c->comm, n_ranks, id, rank));
+  c->comm_ranks = n_ranks;
+  c->comm_rank = rank;
+  int lo = 0, hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = highest priority
+  CU(cudaStreamCreateWithPriority(&c->s_comm, cudaStreamNonBlocking, hi));
+  CU(cudaEventCreateWithFlags(&c->ev_comm_in, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_comm_done, cudaEventDisableTiming));
+  return B2P_OK;
+}
+
+int b2p_comm_destroy(b2p_ctx* c) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (!c->comm) return B2P_OK;
+  DeviceGuard g(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->s_comm) cudaStreamSynchronize(c->s_comm);
+  NCCL_TRY(g_nccl.CommDestroy(c->comm));
+  c->comm = nullptr;
+  c->comm_ranks = 1;
+  return B2P_OK;
+}
+
+// One all-reduce of the by-label partials [n] of every rank, enqueued on the context's stream (asynchronous).
+//   SUM / AVG / COUNT   val (plain sums) and cnt are added (the __sum_state / __sum_merge split of the reference,
+//                       src/query/src/dist_plan/commutativity.rs:85-113); finalise afterwards (b2p_group_finalize_dev)
+//   MIN / MAX           cnt is added, val is reduced with min / max after groups absent on a rank (cnt == 0) were
+//                       set to +inf / -inf; groups absent everywhere end up 0.0 again
+//   STDDEV / STDVAR     inputs are per-rank (cnt, mean, M2 = val): the global mean comes from an all-reduce of
+//                       cnt*mean, then M2 = sum_r [M2_r + cnt_r (mean_r - mean)^2] (commutativity.rs:158-191 merges
+//                       the same state pairwise); on return mean / val hold the merged state on every rank
+int b2p_allreduce_partials_dev(b2p_ctx* c, int32_t agg, double* val, uint32_t* cnt, double* mean, uint64_t n) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (agg < 0 || agg > B2P_AGG_STDVAR) return fail(B2P_E_INVALID, "unknown aggregator %d", agg);
+  if (n == 0) return B2P_OK;
+  if (!val || !cnt) return fail(B2P_E_INVALID, "NULL argument");
+  const bool var = agg == B2P_AGG_STDDEV || agg == B2P_AGG_STDVAR;
+  if (var && !mean) return fail(B2P_E_INVALID, "stddev / stdvar partials need the per-group means");
+  if (!c->comm) {
+    if (c->comm_ranks == 1) return B2P_OK;  // single rank: nothing to merge
+    return fail(B2P_E_INVALID, "no communicator: call b2p_comm_init first");
+  }
+  DeviceGuard g(c->device);
+  uint64_t blocks = (n + 255) / 256;
+  if (blocks > (uint64_t)c->num_sms * 16) blocks = (uint64_t)c->num_sms * 16;
+  if (agg == B2P_AGG_MIN || agg == B2P_AGG_MAX) {
+    minmax_neutral_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(agg == B2P_AGG_MIN, val, cnt, n, 0);
+    NCCL_TRY(g_nccl.GroupStart());
+    NCCL_TRY(g_nccl.AllReduce(val, val, n, Nccl::kFloat64, agg == B2P_AGG_MIN ? Nccl::kMin : Nccl::kMax, c->comm, c->stream));
+    NCCL_TRY(g_nccl.AllReduce(cnt, cnt, n, Nccl::kUint32, Nccl::kSum, c->comm, c->stream));
+    NCCL_TRY(g_nccl.GroupEnd());
+    minmax_neutral_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(agg == B2P_AGG_MIN, val, cnt, n, 1);
+    c->launches += 2;
+  } else if (var) {
+    int rc;
+    if ((rc = c->m_tmp0.ensure(n * 8)) || (rc = c->m_tmp1.ensure(n * 4))) return rc;
+    double* wsum = c->m_tmp0.as<double>();    // cnt_r * mean_r -> global sum
+    uint32_t* cnt_r = c->m_tmp1.as<uint32_t>();  // this rank's counts (cnt itself becomes the global count)
+    variance_merge_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(0, val, cnt, mean, wsum, cnt_r, n);
+    NCCL_TRY(g_nccl.GroupStart());
+    NCCL_TRY(g_nccl.AllReduce(wsum, wsum, n, Nccl::kFloat64, Nccl::kSum, c->comm, c->stream));
+    NCCL_TRY(g_nccl.AllReduce(cnt, cnt, n, Nccl::kUint32, Nccl::kSum, c->comm, c->stream));
+    NCCL_TRY(g_nccl.GroupEnd());
+    variance_merge_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(1, val, cnt, mean, wsum, cnt_r, n);
+    NCCL_TRY(g_nccl.AllReduce(val, val, n, Nccl::kFloat64, Nccl::kSum, c->comm, c->stream));
+    c->launches += 2;
+  } else {
+    NCCL_TRY(g_nccl.GroupStart());
+    NCCL_TRY(g_nccl.AllReduce(val, val, n, Nccl::kFloat64, Nccl::kSum, c->comm, c->stream));
+    NCCL_TRY(g_nccl.AllReduce(cnt, cnt, n, Nccl::kUint32, Nccl::kSum, c->comm, c->stream));
+    NCCL_TRY(g_nccl.GroupEnd());
+  }
+  CU(cudaGetLastError());
+  return B2P_OK;
 }
 
 int b2p_group_finalize_dev(b2p_ctx* c, int32_t agg, double* val, const uint32_t* cnt, uint64_t n) {

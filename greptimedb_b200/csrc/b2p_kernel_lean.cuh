@@ -163,7 +163,9 @@ __device__ __forceinline__ double lean_value(const RangeArgs& a, const LeanRingT
 
 // One aligned group of 32 steps; lane's step is k (window end te, start tlo = te - range, both in the 32-bit
 // domain).  Returns 0, or the reason (> 0) why the series has to go to the second tier.
-template <int FN, bool TAIL, bool FLAGS>
+// GROUPED (fused by-label partials): out_p / vw_p point at this lane's slot of the group's gsum / gcnt row and are
+// updated by read-modify-write — the rows of a group belong to this warp for the whole kernel.
+template <int FN, bool TAIL, bool FLAGS, bool GROUPED = false>
 __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, LeanRingT<FLAGS>& acc,
                                            uint32_t m, uint32_t te, int32_t k, int32_t kl, double* out_p,
                                            uint32_t* vw_p, int lane) {
@@ -265,9 +267,16 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Lea
     ok = false;
     r = 0.0;
   }
-  if (!TAIL || k < (int32_t)a.T) *out_p = r;
-  const uint32_t vw = __ballot_sync(0xffffffffu, ok);
-  if (lane == 0) *vw_p = vw;
+  if constexpr (GROUPED) {
+    if (ok) {  // (ok implies k < T: steps past the grid are trimmed)
+      *out_p = *out_p + r;
+      vw_p[lane] = vw_p[lane] + 1u;
+    }
+  } else {
+    if (!TAIL || k < (int32_t)a.T) *out_p = r;
+    const uint32_t vw = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) *vw_p = vw;
+  }
   return 0;
 }
 
@@ -280,7 +289,7 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Lea
 // non-empty, at most one sample of advance per step (so no cursor start can reach m, see lean_group), and every
 // one of the 64 proportional guesses verified by one vote.  Returns false without side effects when any of that
 // does not hold; the caller then takes the groups one at a time.
-template <int FN, bool FLAGS>
+template <int FN, bool FLAGS, bool GROUPED = false>
 __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, LeanRingT<FLAGS>& acc, uint32_t te,
                                           uint32_t step32, double* out_p, uint32_t* vw_p, int lane) {
   const int32_t top = (int32_t)st.j_cnt - 1;
@@ -345,6 +354,22 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
     st.base_lo = nlo;
   }
   bool ok_a, ok_b;
+  if constexpr (GROUPED) {
+    // the running partials of both steps are requested before the values are computed
+    const double s_a = out_p[0], s_b = out_p[32];
+    const uint32_t c_a = vw_p[lane], c_b = vw_p[lane + 32];
+    const double r_a = lean_value<FN, FLAGS>(a, acc, g_a, q_a, t_lo_a, t_hi_a, te, ok_a);
+    const double r_b = lean_value<FN, FLAGS>(a, acc, g_b, q_b, t_lo_b, t_hi_b, te_b, ok_b);
+    if (ok_a) {
+      out_p[0] = s_a + r_a;
+      vw_p[lane] = c_a + 1u;
+    }
+    if (ok_b) {
+      out_p[32] = s_b + r_b;
+      vw_p[lane + 32] = c_b + 1u;
+    }
+    return true;
+  }
   const double r_a = lean_value<FN, FLAGS>(a, acc, g_a, q_a, t_lo_a, t_hi_a, te, ok_a);
   out_p[0] = r_a;
   const double r_b = lean_value<FN, FLAGS>(a, acc, g_b, q_b, t_lo_b, t_hi_b, te_b, ok_b);
@@ -357,7 +382,7 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
   return true;
 }
 
-template <int FN, bool FLAGS>
+template <int FN, bool FLAGS, bool GROUPED = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_lean_kernel(const RangeArgs a) {
   using LeanRing = LeanRingT<FLAGS>;
   constexpr int RING = kLeanRing;
@@ -401,28 +426,61 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
     if ((uint32_t)lane + 32u < cnt) { cp_async8(stage_t + 256u, pt0 + 32); cp_async8(stage_v + 256u, pv0 + 32); }
     cp_async_commit();
   };
+  // GROUPED: the warp walks whole groups (g_lo + its index, then every total_warps-th), each group's member series
+  // in CSR order; (grp, m, m_end) is the position of the current series, the *_n copies that of the next one
+  uint32_t grp = 0, m = 0, m_end = 0, grp_n = 0, m_n = 0, m_end_n = 0;
+  auto group_first = [&](uint32_t g_from, uint32_t& g_o, uint32_t& m_o, uint32_t& e_o) {  // first non-empty group >= g_from
+    uint32_t g = g_from;
+    uint32_t lo = 0, hi = 0;
+    while (g < a.g_hi) {
+      lo = a.g_off[g];
+      hi = a.g_off[g + 1];
+      if (hi > lo) break;
+      g += total_warps;
+    }
+    g_o = g; m_o = lo; e_o = hi;
+    return g < a.g_hi;
+  };
   uint32_t s = blockIdx.x * kWarpsPerCta + warp;
+  bool have = s < a.n_series;
+  if constexpr (GROUPED) {
+    have = group_first(a.g_lo + s, grp, m, m_end);
+    if (have) s = a.g_members[m];
+  }
   uint64_t row0 = 0, row1 = 0;
-  if (s < a.n_series) {
+  if (have) {
     row0 = a.offsets[s];
     row1 = a.offsets[s + 1];
     issue_block0(row0, row1);
   }
-  for (; s < a.n_series; s += total_warps) {
-    const uint32_t s_next = s + total_warps;
+  while (have) {
+    uint32_t s_next = s + total_warps;
+    bool have_next = s_next < a.n_series;
+    if constexpr (GROUPED) {
+      if (m + 1u < m_end) {
+        grp_n = grp; m_n = m + 1u; m_end_n = m_end;
+        have_next = true;
+      } else {
+        have_next = group_first(grp + total_warps, grp_n, m_n, m_end_n);
+      }
+      if (have_next) s_next = a.g_members[m_n];
+    }
     uint64_t nrow0 = 0, nrow1 = 0;
-    if (s_next < a.n_series) {
+    if (have_next) {
       nrow0 = a.offsets[s_next];
       nrow1 = a.offsets[s_next + 1];
     }
     bool next_issued = false;
     const uint32_t n = (uint32_t)(row1 - row0);
     int defer = ((n == 0u) || (row1 - row0 > 0xfffffff0ull)) ? 3 : 0;  // reason code, 0 = stays on this tier
+    uint32_t k_done = 0;  // GROUPED: steps of this series already added to the partials when it leaves the tier
     if (!defer) {
       const int64_t* ts_s = a.ts + row0;
       const double* val_s = a.val + row0;
-      double* out_p = a.out + (size_t)s * (size_t)T + lane;
-      uint32_t* vw_p = a.valid + (size_t)s * a.Tw;
+      double* out_p = GROUPED ? a.gsum + (size_t)grp * (size_t)T + lane : a.out + (size_t)s * (size_t)T + lane;
+      uint32_t* vw_p = GROUPED ? a.gcnt + (size_t)grp * (size_t)T : a.valid + (size_t)s * a.Tw;
+      constexpr int kVwGroup = GROUPED ? 32 : 1;  // advance of vw_p per 32-step group (counts vs validity words)
+      double* const out_p0 = out_p;
       LeanState st;
       st.j_cnt = 0; st.base_lo = 0; st.base_hi = -1; st.d_lo = 0; st.d_hi = 32; st.phase = 0; st.last_flag = 0;
       uint32_t te = te_lane0;                                      // window end of step k_next + lane
@@ -502,18 +560,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
         const uint32_t t_new = acc.tm(st.j_cnt - 1u);
         // every group whose last window end is older than the newest sample is final
         while (te31 < t_new) {
-          if (B2P_LEAN_PAIR && te31 + step32 < t_new && lean_pair<FN, FLAGS>(a, st, acc, te, step32, out_p, vw_p, lane)) {
+          if (B2P_LEAN_PAIR && te31 + step32 < t_new && lean_pair<FN, FLAGS, GROUPED>(a, st, acc, te, step32, out_p, vw_p, lane)) {
             te += 2u * step32;
             te31 += 2u * step32;
             out_p += 64;
-            vw_p += 2;
+            vw_p += 2 * kVwGroup;
             continue;
           }
-          if ((defer = lean_group<FN, false, FLAGS>(a, st, acc, n, te, 0, 0, out_p, vw_p, lane))) break;
+          // GROUPED: what is added cannot be taken back if a NaN shows up later in the series and lowers the sample
+          // count m the cursor starts are compared with — compare with the samples seen so far instead (m >= j_cnt;
+          // at worst a series is handed on that could have stayed)
+          if ((defer = lean_group<FN, false, FLAGS, GROUPED>(a, st, acc, GROUPED ? st.j_cnt : n, te, 0, 0, out_p, vw_p, lane))) break;
           te += step32;
           te31 += step32;
           out_p += 32;
-          vw_p += 1;
+          vw_p += kVwGroup;
         }
         if (defer) break;
         // a sample past the last window end: every remaining step is final and the rest of the series cannot
@@ -570,13 +631,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
             kl = kl > T - 1 ? T - 1 : kl;
           }
         }
-        for (int32_t k_next = (int32_t)(out_p - (a.out + (size_t)s * (size_t)T + lane)); k_next < T; k_next += 32) {
-          if ((defer = lean_group<FN, true, FLAGS>(a, st, acc, n, te, k_next + lane, kl, out_p, vw_p, lane))) break;
+        for (int32_t k_next = (int32_t)(out_p - out_p0); k_next < T; k_next += 32) {
+          if ((defer = lean_group<FN, true, FLAGS, GROUPED>(a, st, acc, n, te, k_next + lane, kl, out_p, vw_p, lane))) break;
           te += step32;
           out_p += 32;
-          vw_p += 1;
+          vw_p += kVwGroup;
         }
       }
+      k_done = (uint32_t)(out_p - out_p0);
     }
     if (defer && lane == 0) {
 #ifdef B2P_LEAN_DEBUG
@@ -584,6 +646,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
 #endif
       const uint32_t i = atomicAdd(&a.status->w_count, 1u);
       a.w_list[i] = s;
+      if constexpr (GROUPED) a.w_skip[i] = k_done;
     }
     if (!next_issued) {  // the series left the tier before its end of stream
       cp_async_wait<0>();
@@ -591,6 +654,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
     }
     row0 = nrow0;
     row1 = nrow1;
+    s = s_next;
+    have = have_next;
+    if constexpr (GROUPED) {
+      grp = grp_n; m = m_n; m_end = m_end_n;
+    }
     __syncwarp();
   }
   cp_async_wait<0>();

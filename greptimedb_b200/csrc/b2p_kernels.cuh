@@ -34,8 +34,8 @@ struct Status {
   uint32_t w_count;         // series the first tier handed to the warp-per-series kernel
   uint32_t b_count;         // series the warp-per-series kernel handed to its long-window (big ring) instantiation
   uint32_t pad_;
-  unsigned long long arena_used;    // rows claimed in the slow-path arena
-  unsigned long long arena_needed;  // rows that would have been needed
+  unsigned long long arena_used;    // (unused since the arena is split into per-warp regions)
+  unsigned long long arena_needed;  // arena rows that make a region large enough for the longest deferred series
 };
 
 struct RangeArgs {
@@ -65,6 +65,22 @@ struct RangeArgs {
   uint32_t* w_list;
   int32_t use_w_list;  // 0: all series; 1: the series in w_list (w_count); 2: the series in b_list (b_count)
   uint32_t* b_list;    // long-window hand-off: series whose windows do not fit the 256-sample ring
+  // Fused by-label SUM / COUNT partials (sum by (..)(rate(..)) without the [n_series x T] intermediate): when gsum
+  // != nullptr results are not stored per series but added into gsum / gcnt [n_groups x T].  The first tier walks
+  // the series group by group (CSR g_off / g_members, groups [g_lo, g_hi) dealt round-robin to the warps), so a
+  // group's rows belong to one warp and are updated by plain read-modify-write in member order; the later tiers
+  // add the series handed to them with atomics (group of series s = gid[s]).
+  double* gsum;
+  uint32_t* gcnt;
+  const uint32_t* gid;
+  const uint32_t* g_off;      // [n_groups + 1]
+  const uint32_t* g_members;  // [n_series] series ids ordered by (group, series id)
+  uint32_t n_groups, g_lo, g_hi;
+  // a tier that hands a series on after it has already added some of its steps to the partials passes the number of
+  // steps it committed along (parallel to the work lists); the next tier evaluates the series but only adds the rest
+  uint32_t* w_skip;
+  uint32_t* b_skip;
+  uint32_t* slow_skip;
   // slow path plumbing
   Status* status;
   uint32_t* slow_list;
@@ -235,6 +251,12 @@ struct SeriesState {  // warp-uniform
   uint32_t carry_c0; // c0 of the last step of the previous group
   uint32_t last_flag;  // ordinal of the newest set reset/change bit (0 = none yet)
   bool any_nonempty;
+  int32_t k_skip;      // fused by-label partials: steps below this were already added by an earlier tier
+  // fused by-label partials only: the number of samples SeriesNormalize keeps (counted up front), so that the
+  // cursor-overshoot quirk is recognised before a group's values are added (they cannot be taken back), and the flag
+  // that stops the series there
+  uint32_t m_total;
+  bool quirk;
 };
 
 template <bool TS32>
@@ -362,11 +384,22 @@ __device__ __forceinline__ void process_steps(const RangeArgs& a, SeriesState& s
   }
 
   // --- outputs -------------------------------------------------------------------------------------
-  if (active) *out_grp = r;
-  st.vword |= __ballot_sync(0xffffffffu, ok);
-  if ((k_b & 31) == 0 || k_b == (int32_t)a.T) {
-    if (lane == 0) *vw_grp = st.vword;
-    st.vword = 0;
+  if (a.gsum && st.max_c0 >= st.m_total) {  // cursor-overshoot quirk inside this group: the exact slow path decides
+    st.quirk = true;
+    return;
+  }
+  if (a.gsum) {  // fused by-label partials: this tier adds with atomics (out_grp / vw_grp point into gsum / gcnt)
+    if (ok && k >= st.k_skip) {
+      atomicAdd(out_grp, r);
+      atomicAdd(vw_grp + lane, 1u);
+    }
+  } else {
+    if (active) *out_grp = r;
+    st.vword |= __ballot_sync(0xffffffffu, ok);
+    if ((k_b & 31) == 0 || k_b == (int32_t)a.T) {
+      if (lane == 0) *vw_grp = st.vword;
+      st.vword = 0;
+    }
   }
 
   // --- advance the warp-uniform search bases ------------------------------------------------------
@@ -494,9 +527,20 @@ __device__ __forceinline__ void process_group_full(const RangeArgs& a, SeriesSta
     st.carry_c0 = 0;
   }
 
-  *out_grp = r;
-  const uint32_t vw = __ballot_sync(0xffffffffu, ok);
-  if (lane == 0) *vw_grp = vw;
+  if (a.gsum && st.max_c0 >= st.m_total) {
+    st.quirk = true;
+    return;
+  }
+  if (a.gsum) {
+    if (ok && k >= st.k_skip) {
+      atomicAdd(out_grp, r);
+      atomicAdd(vw_grp + lane, 1u);
+    }
+  } else {
+    *out_grp = r;
+    const uint32_t vw = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) *vw_grp = vw;
+  }
 
   st.stride_hi = (nhi - st.base_hi + 16) >> 5;
   st.stride_lo = ((int32_t)(nlo - st.base_lo) + 16) >> 5;
@@ -531,14 +575,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (RING > 256 ? 1 : B2P_FAST_
   for (uint32_t wi = blockIdx.x * kWarpsPerCta + warp; wi < n_work; wi += total_warps) {
     const uint32_t s = a.use_w_list == 2 ? a.b_list[wi] : (a.use_w_list ? a.w_list[wi] : wi);
     const uint64_t row0 = a.offsets[s], row1 = a.offsets[s + 1];
-    double* const out_s = a.out + (size_t)s * (size_t)T;
-    uint32_t* const vw_s = a.valid + (size_t)s * a.Tw;
+    // (fused by-label partials: the "row" of the series is its group's row of gsum / gcnt, one count per step)
+    double* const out_s = a.gsum ? a.gsum + (size_t)a.gid[s] * (size_t)T : a.out + (size_t)s * (size_t)T;
+    uint32_t* const vw_s = a.gsum ? a.gcnt + (size_t)a.gid[s] * (size_t)T : a.valid + (size_t)s * a.Tw;
+    const int vw_step = a.gsum ? 32 : 1;
+    const int32_t k_skip = !a.gsum ? 0 : (a.use_w_list == 2 ? (int32_t)a.b_skip[wi] : (a.use_w_list ? (int32_t)a.w_skip[wi] : 0));
     double* out_grp = out_s + lane;  // this lane's slot in the current aligned 32-step group
     uint32_t* vw_grp = vw_s;         // validity word of the current group
     SeriesState st;
     st.j_cnt = 0; st.base_lo = 0; st.base_hi = -1; st.stride_lo = 1; st.stride_hi = 1;
     st.k_next = 0; st.kf = T; st.vword = 0; st.lrs = 0; st.max_c0 = 0; st.carry_c0 = 0; st.last_flag = 0;
     st.any_nonempty = false;
+    st.k_skip = k_skip;
+    st.m_total = 0xffffffffu;
+    st.quirk = false;
     int64_t last_ts = 0;  // exact (absolute, offset applied) timestamp of the newest surviving sample
     int32_t k_fin = 0;    // steps [0, k_fin) can be evaluated with what is in the ring
     bool defer = false;
@@ -556,10 +606,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (RING > 256 ? 1 : B2P_FAST_
           process_group_full<FN, RING, TS32>(a, st, acc, out_grp, vw_grp, st.k_next, lane);           \
         else                                                                                          \
           process_steps<FN, RING, TS32>(a, st, acc, out_grp, vw_grp, st.k_next, g_end, (KL), lane);   \
+        if (st.quirk) { defer = true; break; }                                                        \
         st.k_next = g_end;                                                                            \
         if ((g_end & 31) == 0) {                                                                      \
           out_grp += 32;                                                                              \
-          vw_grp += 1;                                                                                \
+          vw_grp += vw_step;                                                                          \
         }                                                                                             \
       }                                                                                               \
     } while (0)
@@ -576,6 +627,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (RING > 256 ? 1 : B2P_FAST_
     int32_t rel = 2 * lane - (int32_t)lead;    // this lane's first row of the current block, relative to row0
     const uint32_t n_blk = n_ser + lead;       // rows the blocks have to cover, counted from the aligned start
     uint32_t done = 0;                         // rows covered by completed blocks
+    if (a.gsum) {
+      uint32_t dropped = 0;
+      if (a.filter_nan)
+        for (uint32_t j = lane; j < n_ser; j += 32) dropped += isnan(a.val[row0 + j]) ? 1u : 0u;
+      st.m_total = n_ser - __reduce_add_sync(0xffffffffu, dropped);
+    }
     BlockRegs nxt = load_block(p_ts, p_val, rel, n_ser, tail);
     while (done < n_blk && !defer) {
       const BlockRegs cur = nxt;
@@ -694,18 +751,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (RING > 256 ? 1 : B2P_FAST_
       if (!defer && st.j_cnt > 0 && st.max_c0 >= st.j_cnt) defer = true;
       // "ignore this if all ranges are empty" (range_manipulate.rs:641-643): only the functions that yield
       // Some on an empty window (absent_over_time, quantile_over_time, holt_winters) need the series-level veto.
-      if (FnTraits<FN>::kSomeOnEmpty && !defer && !st.any_nonempty) {
+      if (FnTraits<FN>::kSomeOnEmpty && !defer && !st.any_nonempty && !a.gsum) {
         for (int32_t k = lane; k < T; k += 32) out_s[k] = 0.0;
         for (uint32_t w = lane; w < a.Tw; w += 32) vw_s[w] = 0u;
       }
     }
     if (defer && lane == 0) {
+      const uint32_t done = (uint32_t)(st.k_next > st.k_skip ? st.k_next : st.k_skip);  // steps already added
       if (RING <= 256 && defer_ring && a.b_list != nullptr) {
         const uint32_t i = atomicAdd(&a.status->b_count, 1u);
         a.b_list[i] = s;
+        if (a.gsum) a.b_skip[i] = done;
       } else {
         const uint32_t i = atomicAdd(&a.status->slow_count, 1u);
         a.slow_list[i] = s;
+        if (a.gsum) a.slow_skip[i] = done;
       }
     }
     __syncwarp();
@@ -730,23 +790,28 @@ __global__ void __launch_bounds__(128) range_slow_kernel(const RangeArgs a) {
     const uint32_t s = a.slow_list[w];
     const uint64_t row0 = a.offsets[s], row1 = a.offsets[s + 1];
     const uint64_t n = row1 - row0;
-    double* out_s = a.out + (size_t)s * (size_t)a.T;
-    uint32_t* vw_s = a.valid + (size_t)s * a.Tw;
-    for (int64_t k = lane; k < a.T; k += 32) out_s[k] = 0.0;
-    for (uint32_t q = lane; q < a.Tw; q += 32) vw_s[q] = 0u;
-    if (n == 0) continue;
-    unsigned long long base = 0;
-    if (lane == 0) {
-      base = atomicAdd(&a.status->arena_used, (unsigned long long)n);
-      atomicAdd(&a.status->arena_needed, (unsigned long long)n);
+    const bool fused = a.gsum != nullptr;  // by-label partials: add with atomics, nothing to clear
+    const int64_t k_skip = fused ? (int64_t)a.slow_skip[w] : 0;
+    if (k_skip >= a.T) continue;  // fused: every step was added already (also: finished by an earlier run of this kernel)
+    double* out_s = fused ? a.gsum + (size_t)a.gid[s] * (size_t)a.T : a.out + (size_t)s * (size_t)a.T;
+    uint32_t* vw_s = fused ? a.gcnt + (size_t)a.gid[s] * (size_t)a.T : a.valid + (size_t)s * a.Tw;
+    if (!fused) {
+      for (int64_t k = lane; k < a.T; k += 32) out_s[k] = 0.0;
+      for (uint32_t q = lane; q < a.Tw; q += 32) vw_s[q] = 0u;
     }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base + n > a.arena_cap) {
-      if (lane == 0) atomicExch(&a.status->arena_overflow, 1u);
+    if (n == 0) continue;
+    // every warp of this kernel owns one region of the arena and reuses it series after series; a series longer than
+    // a region is reported (arena_needed = rows that make the regions large enough) and redone after b2p_sync grew it
+    const unsigned long long region = a.arena_cap / total_warps;
+    if (n > region) {
+      if (lane == 0) {
+        atomicMax(&a.status->arena_needed, (unsigned long long)n * total_warps);
+        atomicExch(&a.status->arena_overflow, 1u);
+      }
       continue;
     }
-    int64_t* cts = a.arena_ts + base;
-    double* cval = a.arena_val + base;
+    int64_t* cts = a.arena_ts + (size_t)warp_global * region;
+    double* cval = a.arena_val + (size_t)warp_global * region;
     uint32_t m = 0;
     for (uint64_t r = row0; r < row1; r += 32) {
       const uint64_t rr = r + lane;
@@ -831,11 +896,17 @@ __global__ void __launch_bounds__(128) range_slow_kernel(const RangeArgs a) {
         const unsigned long long pk = wins[k];
         ok = eval_window<FN>(acc, (uint32_t)(pk & 0xffffffffull), (uint32_t)(pk >> 32), a.start + k * a.interval,
                              a.range, a.p0, a.p1, 0.0, r);
-        if (ok) out_s[k] = r;
+        if (ok && !fused) out_s[k] = r;
+        if (ok && fused && k >= k_skip) {
+          atomicAdd(out_s + k, r);
+          atomicAdd(vw_s + k, 1u);
+        }
       }
       const uint32_t word = __ballot_sync(0xffffffffu, ok);
-      if (lane == 0) vw_s[kb >> 5] = word;
+      if (lane == 0 && !fused) vw_s[kb >> 5] = word;
     }
+    // fused: the series is done; a repeat of this kernel (after an arena overflow elsewhere) must not add it again
+    if (fused && lane == 0) a.slow_skip[w] = 0xffffffffu;
   }
 }
 

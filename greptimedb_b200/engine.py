@@ -223,6 +223,55 @@ class Context:
         self._check(self._L.b2p_range_group_sum_dev(self._h, C.byref(p), _ptr(ts), _ptr(val), _ptr(offsets), n_rows,
                                                     n_series, _ptr(gid), n_groups, _ptr(out_sum), _ptr(out_cnt)))
 
+    # group index: an opaque handle (ctypes void pointer) owned by the caller; destroy it with group_index_destroy
+    def group_index_create_dev(self, gid, n_series, n_groups):
+        h = C.c_void_p()
+        self._check(self._L.b2p_group_index_create_dev(self._h, _ptr(gid), n_series, n_groups, C.byref(h)))
+        return h
+
+    def group_index_destroy(self, index):
+        self._L.b2p_group_index_destroy(self._h, index)
+
+    def group_aggregate_indexed_dev(self, agg, vals, valid, index, T, out_val, out_cnt):
+        aid = AGG_IDS[agg] if isinstance(agg, str) else int(agg)
+        self._check(self._L.b2p_group_aggregate_indexed_dev(self._h, aid, _ptr(vals), _ptr(valid), index, T,
+                                                            _ptr(out_val), _ptr(out_cnt)))
+
+    def range_group_sum_indexed_dev(self, p, ts, val, offsets, n_rows, n_series, index, g_lo, g_hi, out_sum, out_cnt):
+        self._check(self._L.b2p_range_group_sum_indexed_dev(self._h, C.byref(p), _ptr(ts), _ptr(val), _ptr(offsets),
+                                                            n_rows, n_series, index, g_lo, g_hi, _ptr(out_sum),
+                                                            _ptr(out_cnt)))
+
+    def range_group_sum_fused(self, p, index) -> bool:
+        return bool(self._L.b2p_range_group_sum_fused(self._h, C.byref(p), index))
+
+    def group_aggregate_partial_dev(self, agg, vals, valid, gid, n_series, n_groups, T, out_val, out_cnt, out_mean=None):
+        aid = AGG_IDS[agg] if isinstance(agg, str) else int(agg)
+        self._check(self._L.b2p_group_aggregate_partial_dev(self._h, aid, _ptr(vals), _ptr(valid), _ptr(gid), n_series,
+                                                            n_groups, T, _ptr(out_val), _ptr(out_cnt), _ptr(out_mean)))
+
+    # multi-GPU: NCCL communicator owned by the context (rank 0 makes the id, every rank calls comm_init)
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self._L.b2p_comm_unique_id(buf, 128))
+        return buf.raw
+
+    def comm_init(self, id_bytes: bytes, n_ranks: int, rank: int):
+        buf = C.create_string_buffer(bytes(id_bytes), 128)
+        self._check(self._L.b2p_comm_init(self._h, buf, 128, n_ranks, rank))
+
+    def comm_destroy(self):
+        self._check(self._L.b2p_comm_destroy(self._h))
+
+    def allreduce_partials_dev(self, agg, val, cnt, mean, n):
+        aid = AGG_IDS[agg] if isinstance(agg, str) else int(agg)
+        self._check(self._L.b2p_allreduce_partials_dev(self._h, aid, _ptr(val), _ptr(cnt), _ptr(mean), n))
+
+    def range_group_sum_allreduce_dev(self, p, ts, val, offsets, n_rows, n_series, index, n_tiles, out_sum, out_cnt):
+        self._check(self._L.b2p_range_group_sum_allreduce_dev(self._h, C.byref(p), _ptr(ts), _ptr(val), _ptr(offsets),
+                                                              n_rows, n_series, index, n_tiles, _ptr(out_sum),
+                                                              _ptr(out_cnt)))
+
     def group_finalize_dev(self, agg, val, cnt, n):
         aid = AGG_IDS[agg] if isinstance(agg, str) else int(agg)
         self._check(self._L.b2p_group_finalize_dev(self._h, aid, _ptr(val), _ptr(cnt), n))

@@ -162,13 +162,63 @@ B2P_API int b2p_instant_select_dev(b2p_ctx* ctx, int64_t start, int64_t end, int
 B2P_API int b2p_group_aggregate_dev(b2p_ctx* ctx, int32_t agg, const double* vals, const uint32_t* valid_words,
                             const uint32_t* gid, uint32_t n_series, uint32_t n_groups, uint64_t T,
                             double* out_val, uint32_t* out_cnt);
-/* Fused range function + by-label partial SUM/COUNT: never materialises [n_series*T].
- * out_sum/out_cnt must be zeroed by the caller (they accumulate, so shards can be chained). */
+/* group -> member-series index of one gid[] assignment (the by-labels of a query do not change between
+ * its batches): built once (radix sort + read-back of the largest group size; synchronises), reused by
+ * b2p_group_aggregate_indexed_dev / b2p_range_group_sum_indexed_dev.  Replaces the hash table of string
+ * keys DataFusion's AggregateExec builds per input row (planner.rs:334-452). */
+typedef struct b2p_group_index b2p_group_index;
+B2P_API int b2p_group_index_create_dev(b2p_ctx* ctx, const uint32_t* gid /* device, [n_series] */, uint32_t n_series,
+                               uint32_t n_groups, b2p_group_index** out_index);
+B2P_API void b2p_group_index_destroy(b2p_ctx* ctx, b2p_group_index* index);
+B2P_API int b2p_group_aggregate_indexed_dev(b2p_ctx* ctx, int32_t agg, const double* vals, const uint32_t* valid_words,
+                                    const b2p_group_index* index, uint64_t T, double* out_val, uint32_t* out_cnt);
+/* sum by (..)(fn(..)): range function + by-label partial SUM / COUNT of groups [g_lo, g_hi), ADDED into
+ * out_sum / out_cnt [n_groups*T] (zero them first; shards, chunks and group ranges chain by accumulation).
+ * rate / increase / delta with the first tier's query shape (32-bit time domain, range >= interval, start >= 0)
+ * and reasonably balanced groups run FUSED: series are walked group by group, a group's rows of out_sum / out_cnt
+ * belong to one warp and are updated in member order — no [n_series*T] intermediate, no atomics on the common
+ * path, asynchronous (b2p_range_group_sum_fused() tells).  At most one fused call is outstanding per context: the
+ * next range call synchronises first.  Everything else takes two passes through context scratch of
+ * n_series*T*8 + n_series*Tw*4 bytes, synchronises in between, and needs the whole group range [0, n_groups). */
+B2P_API int b2p_range_group_sum_indexed_dev(b2p_ctx* ctx, const b2p_range_params* p, const int64_t* ts, const double* val,
+                                    const uint64_t* offsets, uint64_t n_rows, uint32_t n_series,
+                                    const b2p_group_index* index, uint32_t g_lo, uint32_t g_hi, double* out_sum,
+                                    uint32_t* out_cnt);
+B2P_API int b2p_range_group_sum_fused(b2p_ctx* ctx, const b2p_range_params* p, const b2p_group_index* index); /* 1/0 */
+/* Same with a one-off index built from gid (device, [n_series]); synchronous. */
 B2P_API int b2p_range_group_sum_dev(b2p_ctx* ctx, const b2p_range_params* p, const int64_t* ts, const double* val,
                             const uint64_t* offsets, uint64_t n_rows, uint32_t n_series, const uint32_t* gid,
                             uint32_t n_groups, double* out_sum, uint32_t* out_cnt);
-/* After the cross-GPU all-reduce of (sum, cnt): AVG = sum/cnt in place; COUNT = (double)cnt. */
+/* Partial state of one rank / shard for a later cross-rank merge: SUM / AVG -> (sum, cnt); COUNT -> cnt;
+ * MIN / MAX -> (extreme, cnt); STDDEV / STDVAR -> (cnt, mean in out_mean, M2 in out_val). */
+B2P_API int b2p_group_aggregate_partial_dev(b2p_ctx* ctx, int32_t agg, const double* vals, const uint32_t* valid_words,
+                                    const uint32_t* gid, uint32_t n_series, uint32_t n_groups, uint64_t T,
+                                    double* out_val, uint32_t* out_cnt, double* out_mean /* stddev / stdvar, else NULL */);
+/* After the cross-GPU merge: AVG = sum/cnt in place; COUNT = (double)cnt; STDVAR = M2/cnt; STDDEV = sqrt(M2/cnt). */
 B2P_API int b2p_group_finalize_dev(b2p_ctx* ctx, int32_t agg, double* val, const uint32_t* cnt, uint64_t n);
+
+/* ---- multi-GPU (one process / context per GPU): NCCL communicator owned by the context ----------------
+ * Series are hash-sharded over the ranks (the reference hash-partitions on the series key,
+ * series_divide.rs:396-408) and the by-label partials merge with one all-reduce, the analogue of the reference's
+ * __sum_state (datanode) / __sum_merge (frontend) split, src/query/src/dist_plan/commutativity.rs:85-113, 158-191.
+ * libnccl.so.2 is bound with dlopen at the first call (no link dependency; B2P_NCCL_LIB overrides the name).
+ * Rank 0 calls b2p_comm_unique_id and ships the B2P_COMM_ID_BYTES to the other ranks by any means (the reference
+ * would use its own RPC); every rank then calls b2p_comm_init (collective). */
+#define B2P_COMM_ID_BYTES 128
+B2P_API int b2p_comm_unique_id(void* out_id, size_t bytes);
+B2P_API int b2p_comm_init(b2p_ctx* ctx, const void* id, size_t bytes, int n_ranks, int rank);
+B2P_API int b2p_comm_destroy(b2p_ctx* ctx);
+/* In-place merge of every rank's partials [n] on the context's stream (asynchronous): SUM / AVG / COUNT add val and
+ * cnt; MIN / MAX reduce val with min / max (groups absent on a rank are neutral) and add cnt; STDDEV / STDVAR merge
+ * the (cnt, mean, M2 = val) states.  A context without communicator and n_ranks == 1 returns at once. */
+B2P_API int b2p_allreduce_partials_dev(b2p_ctx* ctx, int32_t agg, double* val, uint32_t* cnt, double* mean, uint64_t n);
+/* sum by (..)(fn(..)) over ALL ranks: this rank's fused partials, computed in n_tiles group ranges; each range's rows
+ * of out_sum / out_cnt are all-reduced on a high-priority communication stream as soon as they are complete, while
+ * the next range computes (kernel time of the last tile's all-reduce: b2p_last_kernel_ms(ctx, 4)).  On return
+ * (stream order) out_sum / out_cnt hold the merged partials on every rank. */
+B2P_API int b2p_range_group_sum_allreduce_dev(b2p_ctx* ctx, const b2p_range_params* p, const int64_t* ts,
+                                      const double* val, const uint64_t* offsets, uint64_t n_rows, uint32_t n_series,
+                                      const b2p_group_index* index, int32_t n_tiles, double* out_sum, uint32_t* out_cnt);
 /* rates is the dense matrix of n_hist*n_buckets series (bucket b of histogram h = series
  * h*n_buckets+b, le ascending, last = +Inf).  out [n_hist*T], out_valid_words [n_hist*Tw]. */
 B2P_API int b2p_histogram_quantile_dev(b2p_ctx* ctx, double phi, const double* le, uint32_t n_buckets,

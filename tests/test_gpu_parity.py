@@ -551,13 +551,13 @@ def test_hour_long_windows_take_the_big_ring_not_the_slow_path(ctx):
 def test_several_outstanding_range_calls_each_keep_their_slow_path_verdict(ctx):
     """*_dev range calls are asynchronous and several may be outstanding; a call whose slow path
     ran out of arena must not be forgotten when the next call starts.  Three calls, the first and the last with
-    windows far longer than any ring (slow path, arena overflow), one b2p_sync at the end."""
+    windows far longer than any ring (slow path; the series do not fit a warp's arena region), one b2p_sync at the end."""
     import torch
     from greptimedb_b200 import Context, make_params
     dev = torch.device("cuda:0")
     c = Context(0)   # a fresh context: default 1 M-row arena
     try:
-        S, N, T0 = 1500, 1000, 1_700_000_000_000
+        S, N, T0 = 200, 4000, 1_700_000_000_000   # 4000-row series > one warp's region of the default arena
         ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, 1000, 0, 3)
         offsets = np.arange(S + 1, dtype=np.uint64) * N
         d_ts, d_val = torch.from_numpy(ts).to(dev), torch.from_numpy(val).to(dev)
@@ -568,7 +568,7 @@ def test_several_outstanding_range_calls_each_keep_their_slow_path_verdict(ctx):
         torch.cuda.synchronize()
         for fn, step, rng in queries:
             p = make_params(fn, T0, T0 + (N - 1) * 15_000, step, rng)
-            T = (999 * 15_000) // step + 1
+            T = ((N - 1) * 15_000) // step + 1
             out = torch.full((S * T,), -1.0, dtype=torch.float64, device=dev)
             valid = torch.full((S * ((T + 31) // 32),), -1, dtype=torch.int32, device=dev)
             c.range_eval_dev(p, d_ts, d_val, d_off, S * N, S, out, valid)
@@ -704,6 +704,134 @@ def test_device_api_sum_by_partials_and_finalize(ctx):
     assert (cnt == e_cnt).all()
     rel = np.abs(got - e_avg) / np.maximum(np.abs(e_avg), 1e-300)
     assert rel[e_cnt > 0].max() <= 1e-9
+
+
+def _sum_by_case(S, N, G, resets, nan_every, seed, gid_mode="hash"):
+    T0 = 1_700_000_000_000
+    ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, 1000, resets, seed)
+    if nan_every:
+        val[nan_every // 2::nan_every] = np.nan
+    offsets = np.arange(S + 1, dtype=np.uint64) * N
+    if gid_mode == "hash":
+        from greptimedb_b200 import distributed as D
+        gid = (D.mix32(np.arange(S, dtype=np.uint32)) % np.uint32(G)).astype(np.uint32)
+    else:  # one huge group and many tiny ones
+        gid = np.where(np.arange(S) % 3 == 0, 0, 1 + np.arange(S) % (G - 1)).astype(np.uint32)
+    return T0, ts, val, sid, offsets, gid
+
+
+@pytest.mark.parametrize("fn,resets,nan_every", [("rate", 0, 0), ("rate", 1, 0), ("rate", 0, 9973), ("increase", 1, 7919),
+                                                  ("delta", 0, 0), ("delta", 1, 4099)])
+def test_fused_sum_by_matches_oracle_and_two_pass(ctx, ctx_lean_flags, fn, resets, nan_every):
+    """sum by (..)(rate(..)) without the [S x T] intermediate (b2p_range_group_sum_indexed_dev): the first tier adds
+    group by group, series it hands on (counter resets on the plain variant, NaN samples) are added by the later tiers
+    from the step where the first tier stopped.  Checked against the oracle's rate + group aggregate and against the
+    two-pass composition (range eval into [S x T], then the by-label kernel): counts bit-exact, sums to 1e-9."""
+    import torch
+    from greptimedb_b200 import make_params
+    dev = torch.device("cuda:0")
+    S, N, G = 1500, 700, 97
+    T0, ts, val, sid, offsets, gid = _sum_by_case(S, N, G, resets, nan_every, 11)
+    p = make_params(fn, T0, T0 + (N - 1) * 15_000, 15_000, 300_000)
+    T = N
+    op = orc.make_params(fn, T0, T0 + (N - 1) * 15_000, 15_000, 300_000)
+    e_out, e_valid = orc.range_query(op, ts, val, sid, offsets, threads=8)
+    e_sum, e_cnt = orc.group_aggregate("sum", e_out, e_valid, gid, G)
+    d_ts, d_val = torch.from_numpy(ts).to(dev), torch.from_numpy(val).to(dev)
+    d_off = torch.from_numpy(offsets.astype(np.int64)).to(dev)
+    d_gid = torch.from_numpy(gid.astype(np.int32)).to(dev)
+    for c in (ctx, ctx_lean_flags):
+        c.use_own_stream()
+        torch.cuda.synchronize()
+        ix = c.group_index_create_dev(d_gid, S, G)
+        try:
+            assert c.range_group_sum_fused(p, ix)
+            gsum = torch.zeros(G * T, dtype=torch.float64, device=dev)
+            gcnt = torch.zeros(G * T, dtype=torch.int32, device=dev)
+            # two group ranges chained into the same buffers, like tiles
+            c.range_group_sum_indexed_dev(p, d_ts, d_val, d_off, S * N, S, ix, 0, 40, gsum, gcnt)
+            c.range_group_sum_indexed_dev(p, d_ts, d_val, d_off, S * N, S, ix, 40, G, gsum, gcnt)
+            c.sync()
+            got = gsum.cpu().numpy().reshape(G, T)
+            cnt = gcnt.cpu().numpy().view(np.uint32).reshape(G, T)
+            assert (cnt == e_cnt).all(), f"counts differ at {np.argwhere(cnt != e_cnt)[:4].tolist()}"
+            rel = np.abs(got - e_sum) / np.maximum(np.abs(e_sum), 1e-300)
+            assert rel[e_cnt > 0].max() <= 1e-9
+            assert (got[e_cnt == 0] == 0.0).all()
+        finally:
+            c.group_index_destroy(ix)
+
+
+def test_fused_sum_by_falls_back_on_unbalanced_groups_and_other_functions(ctx):
+    """One group holding a third of all series would serialise on one warp: the call takes the two-pass route (and says
+    so); so do functions without a fused first tier.  Results still match the oracle."""
+    import torch
+    from greptimedb_b200 import make_params
+    dev = torch.device("cuda:0")
+    S, N, G = 6000, 300, 50
+    T0, ts, val, sid, offsets, gid = _sum_by_case(S, N, G, 0, 0, 5, gid_mode="skewed")
+    T = N
+    d_ts, d_val = torch.from_numpy(ts).to(dev), torch.from_numpy(val).to(dev)
+    d_off = torch.from_numpy(offsets.astype(np.int64)).to(dev)
+    d_gid = torch.from_numpy(gid.astype(np.int32)).to(dev)
+    ctx.use_own_stream()
+    torch.cuda.synchronize()
+    ix = ctx.group_index_create_dev(d_gid, S, G)
+    try:
+        for fn in ("rate", "avg_over_time"):
+            p = make_params(fn, T0, T0 + (N - 1) * 15_000, 15_000, 300_000)
+            assert not ctx.range_group_sum_fused(p, ix)
+            gsum = torch.zeros(G * T, dtype=torch.float64, device=dev)
+            gcnt = torch.zeros(G * T, dtype=torch.int32, device=dev)
+            ctx.range_group_sum_indexed_dev(p, d_ts, d_val, d_off, S * N, S, ix, 0, G, gsum, gcnt)
+            ctx.sync()
+            op = orc.make_params(fn, T0, T0 + (N - 1) * 15_000, 15_000, 300_000)
+            e_out, e_valid = orc.range_query(op, ts, val, sid, offsets, threads=8)
+            e_sum, e_cnt = orc.group_aggregate("sum", e_out, e_valid, gid, G)
+            got = gsum.cpu().numpy().reshape(G, T)
+            cnt = gcnt.cpu().numpy().view(np.uint32).reshape(G, T)
+            assert (cnt == e_cnt).all()
+            rel = np.abs(got - e_sum) / np.maximum(np.abs(e_sum), 1e-300)
+            assert rel[e_cnt > 0].max() <= 1e-9
+    finally:
+        ctx.group_index_destroy(ix)
+
+
+def test_fused_sum_by_long_windows_and_quirk_series_add_exactly_once(ctx):
+    """Series that leave the first tier for the long-window ring (1 h windows) or the exact slow kernel (windows beyond
+    any ring; the cursor-overshoot quirk) must contribute every step exactly once."""
+    import torch
+    from greptimedb_b200 import make_params
+    dev = torch.device("cuda:0")
+    T0 = 1_700_000_000_000
+    S, N, G = 96, 1200, 7
+    ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, 1000, 0, 21)
+    offsets = np.arange(S + 1, dtype=np.uint64) * N
+    gid = (np.arange(S) % G).astype(np.uint32)
+    d_ts, d_val = torch.from_numpy(ts).to(dev), torch.from_numpy(val).to(dev)
+    d_off = torch.from_numpy(offsets.astype(np.int64)).to(dev)
+    d_gid = torch.from_numpy(gid.astype(np.int32)).to(dev)
+    ctx.use_own_stream()
+    torch.cuda.synchronize()
+    ix = ctx.group_index_create_dev(d_gid, S, G)
+    try:
+        for rng, step in ((3_600_000, 60_000), (24_000_000, 600_000)):
+            p = make_params("rate", T0, T0 + (N - 1) * 15_000, step, rng)
+            T = ((N - 1) * 15_000) // step + 1
+            gsum = torch.zeros(G * T, dtype=torch.float64, device=dev)
+            gcnt = torch.zeros(G * T, dtype=torch.int32, device=dev)
+            ctx.range_group_sum_indexed_dev(p, d_ts, d_val, d_off, S * N, S, ix, 0, G, gsum, gcnt)
+            ctx.sync()
+            op = orc.make_params("rate", T0, T0 + (N - 1) * 15_000, step, rng)
+            e_out, e_valid = orc.range_query(op, ts, val, sid, offsets, threads=8)
+            e_sum, e_cnt = orc.group_aggregate("sum", e_out, e_valid, gid, G)
+            got = gsum.cpu().numpy().reshape(G, T)
+            cnt = gcnt.cpu().numpy().view(np.uint32).reshape(G, T)
+            assert (cnt == e_cnt).all(), (rng, np.argwhere(cnt != e_cnt)[:4].tolist())
+            rel = np.abs(got - e_sum) / np.maximum(np.abs(e_sum), 1e-300)
+            assert rel[e_cnt > 0].max() <= 1e-9
+    finally:
+        ctx.group_index_destroy(ix)
 
 
 def test_column_reduce_config5_shape(ctx):
