@@ -206,12 +206,52 @@ struct HistArgs {
   uint32_t* out_valid;
 };
 
-__global__ void __launch_bounds__(256) histogram_quantile_kernel(const HistArgs a) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t tiles = (a.T + 31) / 32;
-  const uint64_t total = (uint64_t)a.n_hist * tiles;
+// The row evaluation of HistogramFold::evaluate_row (histogram_fold.rs:1046-1118) once the monotonised counters
+// c[0..B) of the row are known through `get(b)`, its total and the per-query bucket checks.
+template <class Get>
+__device__ __forceinline__ double histogram_row(const HistArgs& a, bool bucket_sorted, bool last_inf, double total_c, Get get) {
   const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
   const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+  if (a.B <= 1) return kNaN;
+  if (!last_inf) return kNaN;  // Err("last bucket should be +Inf") -> unwrap_or(NaN), :806
+  if (a.phi < 0.0) return -kInf;
+  if (a.phi > 1.0) return kInf;
+  if (isnan(a.phi)) return kNaN;
+  if (!bucket_sorted) return kNaN;
+  const double expected_pos = total_c * a.phi;
+  // first bucket whose counter is >= expected_pos: the counters are non-decreasing, so bisect
+  uint32_t lo = 0, hi = a.B;  // answer in [lo, hi]; hi == B: none (cannot happen: c[B-1] = total >= pos for phi <= 1)
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (get(mid) < expected_pos) lo = mid + 1; else hi = mid;
+  }
+  const uint32_t fit = lo;
+  if (fit >= a.B - 1) return a.le[a.B - 2];
+  const double upper_count = get(fit);
+  const double upper_bound = a.le[fit];
+  double lower_bound = fmin(a.le[0], 0.0), lower_count = 0.0;
+  if (fit > 0) {
+    lower_bound = a.le[fit - 1];
+    lower_count = get(fit - 1);
+  }
+  if (fabs(upper_count - lower_count) < 1e-10) return kNaN;
+  return lower_bound + (upper_bound - lower_bound) / (upper_count - lower_count) * (expected_pos - lower_count);
+}
+
+constexpr int kHistWarps = 4;          // warps per CTA of K5
+constexpr int kHistSmemBuckets = 64;   // rows with up to this many buckets keep their counters in shared memory
+
+// One pass over HBM: the warp reads the B rate segments of its (histogram, 32-step tile) once (coalesced 256 bytes per
+// bucket, eight requests in flight per lane), monotonises them on the way into shared memory ([bucket][lane], conflict
+// free), then every lane bisects its own column.  Algorithmic traffic: 8 B x B + B bits read, 8 B + 1 bit written per
+// (histogram, step).  Rows with more than kHistSmemBuckets buckets re-read the segments for the bisection (L2 hits).
+__global__ void __launch_bounds__(kHistWarps * 32) histogram_quantile_kernel(const HistArgs a) {
+  extern __shared__ __align__(16) unsigned char hist_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* col = reinterpret_cast<double*>(hist_smem) + (size_t)warp * kHistSmemBuckets * 32 + lane;  // col[b * 32]
+  const uint64_t tiles = (a.T + 31) / 32;
+  const uint64_t total = (uint64_t)a.n_hist * tiles;
+  const bool in_smem = a.B <= (uint32_t)kHistSmemBuckets;
   // bucket checks are identical for every row (histogram_fold.rs:1047-1073)
   bool bucket_sorted = true;
   for (uint32_t b = 0; b + 1 < a.B; ++b) bucket_sorted &= (a.le[b] <= a.le[b + 1]);
@@ -223,56 +263,45 @@ __global__ void __launch_bounds__(256) histogram_quantile_kernel(const HistArgs 
     const uint64_t k = tile * 32 + lane;
     const bool in = k < a.T;
     const size_t s0 = (size_t)h * a.B;
-    // completeness + pass 1: total of the monotonised counters
+    // a row exists iff all B buckets are present at that step: lanes fetch the validity words of 32 buckets at a time
     uint32_t all = 0xffffffffu;
-    double prev = 0.0, total_c = 0.0;
-    for (uint32_t b = 0; b < a.B; ++b) {
-      all &= a.valid[(s0 + b) * a.Tw + tile];
-      if (in) {
-        const double v = a.rates[(s0 + b) * a.T + k];
-        double c = isfinite(v) ? v : prev;
-        if (b > 0 && c < prev) c = prev;
-        prev = c;
-        total_c = c;
+    for (uint32_t b0 = 0; b0 < a.B; b0 += 32) {
+      const uint32_t wv = (b0 + lane < a.B) ? a.valid[(s0 + b0 + lane) * a.Tw + tile] : 0xffffffffu;
+      all &= __reduce_and_sync(0xffffffffu, wv);
+    }
+    const double* seg = a.rates + s0 * a.T + (in ? k : 0);
+    double prev = 0.0;
+    for (uint32_t b0 = 0; b0 < a.B; b0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (b0 + u < a.B && in) ? __ldcs(seg + (size_t)(b0 + u) * a.T) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (b0 + u < a.B) {
+          double c = isfinite(v[u]) ? v[u] : prev;  // non-finite -> previous, decreasing -> previous (:1074-1092)
+          if (b0 + u > 0 && c < prev) c = prev;
+          prev = c;
+          if (in_smem) col[(b0 + u) * 32] = c;
+        }
       }
     }
     const bool ok = in && ((all >> lane) & 1u);
     double r = 0.0;
     if (ok) {
-      if (a.B <= 1) r = kNaN;
-      else if (!last_inf) r = kNaN;  // Err("last bucket should be +Inf") -> unwrap_or(NaN), :806
-      else if (a.phi < 0.0) r = -kInf;
-      else if (a.phi > 1.0) r = kInf;
-      else if (isnan(a.phi)) r = kNaN;
-      else if (!bucket_sorted) r = kNaN;
-      else {
-        const double expected_pos = total_c * a.phi;
-        // pass 2: first bucket whose counter >= expected_pos
-        double pc = 0.0, lower_count = 0.0, upper_count = 0.0;
-        uint32_t fit = a.B;
-        prev = 0.0;
-        for (uint32_t b = 0; b < a.B; ++b) {
-          const double v = a.rates[(s0 + b) * a.T + k];
-          double c = isfinite(v) ? v : prev;
-          if (b > 0 && c < prev) c = prev;
-          prev = c;
-          if (!(c < expected_pos)) {
-            fit = b;
-            upper_count = c;
-            lower_count = pc;
-            break;
+      if (in_smem) {
+        r = histogram_row(a, bucket_sorted, last_inf, prev, [&](uint32_t b) { return col[b * 32]; });
+      } else {
+        // counters of bucket b on demand: the running maximum needs the buckets before it — walk (rare, wide rows)
+        r = histogram_row(a, bucket_sorted, last_inf, prev, [&](uint32_t b) {
+          double p = 0.0;
+          for (uint32_t q = 0; q <= b; ++q) {
+            const double x = seg[(size_t)q * a.T];
+            double c = isfinite(x) ? x : p;
+            if (q > 0 && c < p) c = p;
+            p = c;
           }
-          pc = c;
-        }
-        if (fit >= a.B - 1) {
-          r = a.le[a.B - 2];
-        } else {
-          const double upper_bound = a.le[fit];
-          double lower_bound = fmin(a.le[0], 0.0);
-          if (fit > 0) lower_bound = a.le[fit - 1]; else lower_count = 0.0;
-          if (fabs(upper_count - lower_count) < 1e-10) r = kNaN;
-          else r = lower_bound + (upper_bound - lower_bound) / (upper_count - lower_count) * (expected_pos - lower_count);
-        }
+          return p;
+        });
       }
     }
     if (in) a.out[(size_t)h * a.T + k] = r;

@@ -160,8 +160,9 @@ struct b2p_ctx {
   // multi-GPU (one process per GPU): communicator of the by-label all-reduce, its stream and join event
   Nccl::comm_t comm = nullptr;
   int comm_ranks = 1, comm_rank = 0;
+  long long comm_headstart_cycles = 60000;  // ~30 us at 1.965 GHz (B2P_COMM_HEADSTART_US overrides)
   cudaStream_t s_comm = nullptr;
-  cudaEvent_t ev_comm_in = nullptr, ev_comm_done = nullptr;
+  cudaEvent_t ev_comm_in = nullptr, ev_comm_done = nullptr, ev_comm_go = nullptr;
   DevBuf m_tmp0, m_tmp1;             // scratch of the variance merge
   DevBuf w_skip, b_skip, slow_skip;  // fused by-label partials: steps already added, parallel to the work lists
   bool fused_pending = false;        // a fused call is outstanding: its work lists must survive until b2p_sync
@@ -359,7 +360,7 @@ int launch_lean_if_supported(b2p_ctx* c, const RangeArgs& a, bool with_flags) {
 // gsum / gcnt (range_lean_kernel<FN, FLAGS, GROUPED = true>).
 template <int FN, bool FLAGS>
 int launch_lean_grouped(b2p_ctx* c, const RangeArgs& a) {
-  constexpr size_t smem = lean_smem_bytes();
+  constexpr size_t smem = lean_grouped_smem_bytes();
   auto kern = range_lean_kernel<FN, FLAGS, true>;
   static int cached_nb[16] = {};  // per device
   int& cached = cached_nb[c->device & 15];
@@ -562,6 +563,7 @@ b2p_ctx* b2p_create(int device) {
   if (const char* e = getenv("B2P_DISABLE_LEAN_TIER")) c->lean_tier = !(e[0] == '1');
   if (const char* e = getenv("B2P_LEAN_ADAPTIVE")) c->lean_adaptive = !(e[0] == '0');
   if (const char* e = getenv("B2P_LEAN_FORCE_FLAGS")) c->lean_force_flags = (e[0] == '1');
+  if (const char* e = getenv("B2P_COMM_HEADSTART_US")) c->comm_headstart_cycles = (long long)(atof(e) * 1965.0);
   if (const char* e = getenv("B2P_ARENA_ROWS")) c->arena_rows_wanted = (size_t)strtoull(e, nullptr, 10);
   return c;
 }
@@ -574,6 +576,7 @@ void b2p_destroy(b2p_ctx* c) {
   if (c->s_comm) cudaStreamDestroy(c->s_comm);
   if (c->ev_comm_in) cudaEventDestroy(c->ev_comm_in);
   if (c->ev_comm_done) cudaEventDestroy(c->ev_comm_done);
+  if (c->ev_comm_go) cudaEventDestroy(c->ev_comm_go);
   for (DevBuf* b : {&c->w_skip, &c->b_skip, &c->slow_skip, &c->m_tmp0, &c->m_tmp1}) b->release();
   for (DevBuf* b : {&c->slow_list, &c->w_list, &c->b_list, &c->arena_ts, &c->arena_val, &c->win_scratch, &c->h_ts, &c->h_val, &c->h_sid,
                     &c->h_off, &c->h_out, &c->h_valid, &c->h_aux0, &c->h_aux1, &c->h_aux2, &c->h_aux3,
@@ -627,6 +630,14 @@ double b2p_last_kernel_ms(b2p_ctx* c, int stage) {
   return (double)ms;
 }
 
+__global__ void comm_marker_kernel() {}
+// holds the compute stream back for a few microseconds so that the all-reduce released at the same instant on the
+// communication stream has its CTAs placed before the persistent range kernel asks for every SM
+__global__ void comm_headstart_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {}
+}
+
 // Launches every tier of one range call (first tier when `used_lean`/`thread_tier`, warp-per-series kernel, its
 // long-window instantiation, exact slow kernel) on the context's stream.
 static int launch_range_tiers(b2p_ctx* c, int fn, RangeArgs a, bool thread_tier, bool used_lean, int lean_mode,
@@ -636,7 +647,7 @@ static int launch_range_tiers(b2p_ctx* c, int fn, RangeArgs a, bool thread_tier,
     CU(cudaMemsetAsync(a.status, 0, sizeof(Status), c->stream));
   } else {  // a further tile of the same fused call: new work lists, same verdict (overflow / arena fields stay)
     CU(cudaMemsetAsync(&a.status->slow_count, 0, sizeof(uint32_t), c->stream));
-    CU(cudaMemsetAsync(&a.status->w_count, 0, 2 * sizeof(uint32_t), c->stream));
+    CU(cudaMemsetAsync(&a.status->w_count, 0, 3 * sizeof(uint32_t), c->stream));  // w_count, b_count, g_next
   }
   stage_begin(c, 1);
   if (thread_tier) {
@@ -768,6 +779,7 @@ struct GroupTarget {
 // the query shape, and not switched off by the adaptive policy; groups balanced enough for group-exclusive warps)
 static bool fused_group_ok(b2p_ctx* c, const b2p_range_params* p, int64_t T, const b2p_group_index* idx) {
   if (!lean_grouped_fn(p->fn_id) || c->thread_tier) return false;
+  if (T > 32 * (int64_t)kLeanFullWords) return false;  // per-warp word counters of the first tier
   RangeArgs a{};
   a.start = p->start; a.end = p->end; a.interval = p->interval; a.range = p->range;
   a.T = T;
@@ -882,6 +894,14 @@ static int range_call(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, 
         const size_t off = (size_t)a.g_lo * (size_t)T, cnt_n = (size_t)(a.g_hi - a.g_lo) * (size_t)T;
         CU(cudaEventRecord(c->ev_comm_in, c->stream));
         CU(cudaStreamWaitEvent(c->s_comm, c->ev_comm_in, 0));
+        // The next tile's kernels are released by a marker that sits directly IN FRONT of the all-reduce on the
+        // communication stream: when they become runnable the (few) NCCL CTAs are already next in line on the
+        // high-priority stream and get their SMs first; the persistent first-tier kernel fills what is left and its
+        // dynamic group counter keeps late CTAs from becoming a tail.
+        comm_marker_kernel<<<1, 32, 0, c->s_comm>>>();
+        CU(cudaEventRecord(c->ev_comm_go, c->s_comm));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_comm_go, 0));
+        if (c->comm_headstart_cycles > 0) comm_headstart_kernel<<<1, 32, 0, c->stream>>>(c->comm_headstart_cycles);
         stage_begin_on(c, 4, c->s_comm);
         NCCL_TRY(g_nccl.GroupStart());
         NCCL_TRY(g_nccl.AllReduce(a.gsum + off, a.gsum + off, cnt_n, Nccl::kFloat64, Nccl::kSum, c->comm, c->s_comm));
@@ -1193,6 +1213,10 @@ int b2p_comm_init(b2p_ctx* c, const void* id_bytes, size_t bytes, int n_ranks, i
   DeviceGuard g(c->device);
   Nccl::unique_id id;
   memcpy(&id, id_bytes, sizeof id);
+  // the tile all-reduces run next to the persistent range kernel: keep their footprint to a few SMs (an explicit
+  // NCCL_MAX_CTAS / NCCL_MAX_NCHANNELS of the caller wins)
+  setenv("NCCL_MAX_CTAS", "16", 0);
+  setenv("NCCL_MAX_NCHANNELS", "16", 0);
   NCCL_TRY(g_nccl.CommInitRank(&c->comm, n_ranks, id, rank));
   c->comm_ranks = n_ranks;
   c->comm_rank = rank;
@@ -1201,6 +1225,7 @@ int b2p_comm_init(b2p_ctx* c, const void* id_bytes, size_t bytes, int n_ranks, i
   CU(cudaStreamCreateWithPriority(&c->s_comm, cudaStreamNonBlocking, hi));
   CU(cudaEventCreateWithFlags(&c->ev_comm_in, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_comm_done, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_comm_go, cudaEventDisableTiming));
   return B2P_OK;
 }
 
@@ -1260,12 +1285,33 @@ int b2p_allreduce_partials_dev(b2p_ctx* c, int32_t agg, double* val, uint32_t* c
     NCCL_TRY(g_nccl.AllReduce(val, val, n, Nccl::kFloat64, Nccl::kSum, c->comm, c->stream));
     c->launches += 2;
   } else {
+    stage_begin(c, 4);
     NCCL_TRY(g_nccl.GroupStart());
     NCCL_TRY(g_nccl.AllReduce(val, val, n, Nccl::kFloat64, Nccl::kSum, c->comm, c->stream));
     NCCL_TRY(g_nccl.AllReduce(cnt, cnt, n, Nccl::kUint32, Nccl::kSum, c->comm, c->stream));
     NCCL_TRY(g_nccl.GroupEnd());
+    stage_end(c, 4);
   }
   CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+// config 5 (wide avg_over_time): per-column (sum f64, count u64) of every rank added in place
+int b2p_allreduce_columns_dev(b2p_ctx* c, double* sum, uint64_t* cnt, uint32_t n_cols) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (n_cols == 0) return B2P_OK;
+  if (!sum || !cnt) return fail(B2P_E_INVALID, "NULL argument");
+  if (!c->comm) {
+    if (c->comm_ranks == 1) return B2P_OK;
+    return fail(B2P_E_INVALID, "no communicator: call b2p_comm_init first");
+  }
+  DeviceGuard g(c->device);
+  stage_begin(c, 4);
+  NCCL_TRY(g_nccl.GroupStart());
+  NCCL_TRY(g_nccl.AllReduce(sum, sum, n_cols, Nccl::kFloat64, Nccl::kSum, c->comm, c->stream));
+  NCCL_TRY(g_nccl.AllReduce(cnt, cnt, n_cols, Nccl::kUint64, Nccl::kSum, c->comm, c->stream));
+  NCCL_TRY(g_nccl.GroupEnd());
+  stage_end(c, 4);
   return B2P_OK;
 }
 
@@ -1293,11 +1339,17 @@ int b2p_histogram_quantile_dev(b2p_ctx* c, double phi, const double* le, uint32_
   a.phi = phi; a.le = le; a.B = n_buckets; a.rates = rates; a.valid = valid_words; a.n_hist = n_hist; a.T = T;
   a.Tw = (uint32_t)((T + 31) / 32); a.out = out; a.out_valid = out_valid_words;
   const uint64_t warps = (uint64_t)n_hist * ((T + 31) / 32);
-  uint64_t blocks = (warps + 7) / 8;
-  const uint64_t cap = (uint64_t)c->num_sms * 32;
+  uint64_t blocks = (warps + kHistWarps - 1) / kHistWarps;
+  const uint64_t cap = (uint64_t)c->num_sms * 3;  // 64 KB of counters per CTA: three CTAs per SM
   if (blocks > cap) blocks = cap;
+  constexpr size_t smem = (size_t)kHistWarps * kHistSmemBuckets * 32 * 8;
+  static bool attr_set[16] = {};
+  if (!attr_set[c->device & 15]) {
+    CU(cudaFuncSetAttribute(histogram_quantile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[c->device & 15] = true;
+  }
   stage_begin(c, 3);
-  histogram_quantile_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(a);
+  histogram_quantile_kernel<<<(unsigned)blocks, kHistWarps * 32, smem, c->stream>>>(a);
   c->launches++;
   stage_end(c, 3);
   CU(cudaGetLastError());

@@ -39,7 +39,12 @@ namespace b2p {
 constexpr int kLeanRing = 256;
 // dynamic shared memory of one CTA: value ring + mirrored timestamp ring + reciprocal table + staging (two 64-row
 // blocks per warp and column) + bit words
-constexpr size_t lean_smem_bytes() {
+// GROUPED (fused by-label partials): per-warp counters "members of the current group whose 32-step word k/32 was valid
+// throughout" — the by far most common word; they are added to the count row when the warp leaves the group, so the
+// hot path updates the per-step counts in global memory only for the few partially valid words
+constexpr int kLeanFullWords = 256;  // => T <= 8192 eval steps on the fused path (host gate)
+__host__ __device__ constexpr size_t lean_grouped_smem_bytes();
+__host__ __device__ constexpr size_t lean_smem_bytes() {
   return (size_t)kWarpsPerCta * kLeanRing * 16 + kRcpTable * 8 + (size_t)kWarpsPerCta * 2 * 64 * 16 +
          (size_t)kWarpsPerCta * (kLeanRing / 32) * 4;
 }
@@ -168,7 +173,7 @@ __device__ __forceinline__ double lean_value(const RangeArgs& a, const LeanRingT
 template <int FN, bool TAIL, bool FLAGS, bool GROUPED = false>
 __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, LeanRingT<FLAGS>& acc,
                                            uint32_t m, uint32_t te, int32_t k, int32_t kl, double* out_p,
-                                           uint32_t* vw_p, int lane) {
+                                           uint32_t* vw_p, int lane, uint32_t* full_p = nullptr) {
   const uint32_t rng = (uint32_t)a.range;
   const uint32_t tlo = te - rng;
   const int32_t top = (int32_t)st.j_cnt - 1;
@@ -268,8 +273,11 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Lea
     r = 0.0;
   }
   if constexpr (GROUPED) {
-    if (ok) {  // (ok implies k < T: steps past the grid are trimmed)
-      *out_p = *out_p + r;
+    const uint32_t vw = __ballot_sync(0xffffffffu, ok);
+    if (ok) *out_p = *out_p + r;  // (ok implies k < T: steps past the grid are trimmed)
+    if (vw == 0xffffffffu) {
+      if (lane == 0) *full_p += 1u;
+    } else if (ok) {
       vw_p[lane] = vw_p[lane] + 1u;
     }
   } else {
@@ -291,7 +299,8 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Lea
 // does not hold; the caller then takes the groups one at a time.
 template <int FN, bool FLAGS, bool GROUPED = false>
 __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, LeanRingT<FLAGS>& acc, uint32_t te,
-                                          uint32_t step32, double* out_p, uint32_t* vw_p, int lane) {
+                                          uint32_t step32, double* out_p, uint32_t* vw_p, int lane,
+                                          uint32_t* full_p = nullptr) {
   const int32_t top = (int32_t)st.j_cnt - 1;
   // uniform gates; the last two keep every read below the newest sample (slot top), i.e. on written slots
   if (st.phase != 1u || st.d_lo > 32u || st.base_hi + 2 * (int32_t)st.d_hi >= top || st.base_lo + 2u * st.d_lo > (uint32_t)top)
@@ -357,16 +366,27 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
   if constexpr (GROUPED) {
     // the running partials of both steps are requested before the values are computed
     const double s_a = out_p[0], s_b = out_p[32];
-    const uint32_t c_a = vw_p[lane], c_b = vw_p[lane + 32];
     const double r_a = lean_value<FN, FLAGS>(a, acc, g_a, q_a, t_lo_a, t_hi_a, te, ok_a);
     const double r_b = lean_value<FN, FLAGS>(a, acc, g_b, q_b, t_lo_b, t_hi_b, te_b, ok_b);
-    if (ok_a) {
-      out_p[0] = s_a + r_a;
-      vw_p[lane] = c_a + 1u;
-    }
-    if (ok_b) {
-      out_p[32] = s_b + r_b;
-      vw_p[lane + 32] = c_b + 1u;
+    const uint32_t vw_a = __ballot_sync(0xffffffffu, ok_a), vw_b = __ballot_sync(0xffffffffu, ok_b);
+    if (ok_a) out_p[0] = s_a + r_a;
+    if (ok_b) out_p[32] = s_b + r_b;
+    if ((vw_a & vw_b) == 0xffffffffu) {  // both words valid throughout: two per-warp counters instead of 64 counts
+      if (lane == 0) {
+        full_p[0] += 1u;
+        full_p[1] += 1u;
+      }
+    } else {
+      if (vw_a == 0xffffffffu) {
+        if (lane == 0) full_p[0] += 1u;
+      } else if (ok_a) {
+        vw_p[lane] = vw_p[lane] + 1u;
+      }
+      if (vw_b == 0xffffffffu) {
+        if (lane == 0) full_p[1] += 1u;
+      } else if (ok_b) {
+        vw_p[lane + 32] = vw_p[lane + 32] + 1u;
+      }
     }
     return true;
   }
@@ -407,6 +427,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
   acc.init_addresses();
   acc.flags_sa = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable + kWarpsPerCta * 256) + (uint32_t)warp * (RING / 32) * 4u;
   acc.no_flags = true;
+  // GROUPED: per-warp "valid throughout" counters of the current group, one per 32-step word (behind everything else)
+  uint32_t* const full_w = reinterpret_cast<uint32_t*>(smem_raw + lean_smem_bytes()) + warp * kLeanFullWords;
+  if constexpr (GROUPED) {
+    for (int i = lane; i < kLeanFullWords; i += 32) full_w[i] = 0u;
+    __syncwarp();
+  }
   const uint32_t total_warps = gridDim.x * kWarpsPerCta;
   const int32_t T = (int32_t)a.T;
   const long long tb_off = a.tb - a.offset;  // rel = ts + offset - tb
@@ -426,17 +452,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
     if ((uint32_t)lane + 32u < cnt) { cp_async8(stage_t + 256u, pt0 + 32); cp_async8(stage_v + 256u, pv0 + 32); }
     cp_async_commit();
   };
-  // GROUPED: the warp walks whole groups (g_lo + its index, then every total_warps-th), each group's member series
-  // in CSR order; (grp, m, m_end) is the position of the current series, the *_n copies that of the next one
+  // GROUPED: the warp walks whole groups, each group's member series in CSR order; groups are dealt out dynamically
+  // (one atomic counter per launch) so that CTAs which start late — the all-reduce of the previous tile may hold a few
+  // SMs — simply take fewer groups.  (grp, m, m_end) is the position of the current series, the *_n copies that of
+  // the next one.
   uint32_t grp = 0, m = 0, m_end = 0, grp_n = 0, m_n = 0, m_end_n = 0;
-  auto group_first = [&](uint32_t g_from, uint32_t& g_o, uint32_t& m_o, uint32_t& e_o) {  // first non-empty group >= g_from
-    uint32_t g = g_from;
-    uint32_t lo = 0, hi = 0;
-    while (g < a.g_hi) {
+  auto group_first = [&](uint32_t& g_o, uint32_t& m_o, uint32_t& e_o) {  // next non-empty group from the counter
+    uint32_t g = a.g_hi, lo = 0, hi = 0;
+    for (;;) {
+      uint32_t t = 0;
+      if (lane == 0) t = atomicAdd(&a.status->g_next, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      g = a.g_lo + t;
+      if (g >= a.g_hi || t >= a.g_hi) { g = a.g_hi; break; }
       lo = a.g_off[g];
       hi = a.g_off[g + 1];
       if (hi > lo) break;
-      g += total_warps;
     }
     g_o = g; m_o = lo; e_o = hi;
     return g < a.g_hi;
@@ -444,7 +475,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
   uint32_t s = blockIdx.x * kWarpsPerCta + warp;
   bool have = s < a.n_series;
   if constexpr (GROUPED) {
-    have = group_first(a.g_lo + s, grp, m, m_end);
+    have = group_first(grp, m, m_end);
     if (have) s = a.g_members[m];
   }
   uint64_t row0 = 0, row1 = 0;
@@ -461,7 +492,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
         grp_n = grp; m_n = m + 1u; m_end_n = m_end;
         have_next = true;
       } else {
-        have_next = group_first(grp + total_warps, grp_n, m_n, m_end_n);
+        have_next = group_first(grp_n, m_n, m_end_n);
       }
       if (have_next) s_next = a.g_members[m_n];
     }
@@ -480,6 +511,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
       double* out_p = GROUPED ? a.gsum + (size_t)grp * (size_t)T + lane : a.out + (size_t)s * (size_t)T + lane;
       uint32_t* vw_p = GROUPED ? a.gcnt + (size_t)grp * (size_t)T : a.valid + (size_t)s * a.Tw;
       constexpr int kVwGroup = GROUPED ? 32 : 1;  // advance of vw_p per 32-step group (counts vs validity words)
+      uint32_t* full_p = full_w;
       double* const out_p0 = out_p;
       LeanState st;
       st.j_cnt = 0; st.base_lo = 0; st.base_hi = -1; st.d_lo = 0; st.d_hi = 32; st.phase = 0; st.last_flag = 0;
@@ -560,21 +592,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
         const uint32_t t_new = acc.tm(st.j_cnt - 1u);
         // every group whose last window end is older than the newest sample is final
         while (te31 < t_new) {
-          if (B2P_LEAN_PAIR && te31 + step32 < t_new && lean_pair<FN, FLAGS, GROUPED>(a, st, acc, te, step32, out_p, vw_p, lane)) {
+          if (B2P_LEAN_PAIR && te31 + step32 < t_new && lean_pair<FN, FLAGS, GROUPED>(a, st, acc, te, step32, out_p, vw_p, lane, full_p)) {
             te += 2u * step32;
             te31 += 2u * step32;
             out_p += 64;
             vw_p += 2 * kVwGroup;
+            full_p += 2;
             continue;
           }
           // GROUPED: what is added cannot be taken back if a NaN shows up later in the series and lowers the sample
           // count m the cursor starts are compared with — compare with the samples seen so far instead (m >= j_cnt;
           // at worst a series is handed on that could have stayed)
-          if ((defer = lean_group<FN, false, FLAGS, GROUPED>(a, st, acc, GROUPED ? st.j_cnt : n, te, 0, 0, out_p, vw_p, lane))) break;
+          if ((defer = lean_group<FN, false, FLAGS, GROUPED>(a, st, acc, GROUPED ? st.j_cnt : n, te, 0, 0, out_p, vw_p, lane, full_p))) break;
           te += step32;
           te31 += step32;
           out_p += 32;
           vw_p += kVwGroup;
+          full_p += 1;
         }
         if (defer) break;
         // a sample past the last window end: every remaining step is final and the rest of the series cannot
@@ -632,10 +666,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
           }
         }
         for (int32_t k_next = (int32_t)(out_p - out_p0); k_next < T; k_next += 32) {
-          if ((defer = lean_group<FN, true, FLAGS, GROUPED>(a, st, acc, n, te, k_next + lane, kl, out_p, vw_p, lane))) break;
+          if ((defer = lean_group<FN, true, FLAGS, GROUPED>(a, st, acc, n, te, k_next + lane, kl, out_p, vw_p, lane, full_p))) break;
           te += step32;
           out_p += 32;
           vw_p += kVwGroup;
+          full_p += 1;
         }
       }
       k_done = (uint32_t)(out_p - out_p0);
@@ -657,11 +692,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
     s = s_next;
     have = have_next;
     if constexpr (GROUPED) {
+      if (!have_next || grp_n != grp) {
+        // leaving the group: its "valid throughout" counters join the count row (coalesced, one word at a time)
+        __syncwarp();
+        uint32_t* gc = a.gcnt + (size_t)grp * (size_t)T + lane;
+        for (uint32_t w = 0; w < a.Tw; ++w) {
+          const uint32_t c = full_w[w];
+          if (c != 0u && (int32_t)(w * 32u + (uint32_t)lane) < T) gc[w * 32u] += c;
+        }
+        __syncwarp();
+        for (uint32_t w = lane; w < a.Tw; w += 32) full_w[w] = 0u;
+      }
       grp = grp_n; m = m_n; m_end = m_end_n;
     }
     __syncwarp();
   }
   cp_async_wait<0>();
 }
+
+__host__ __device__ constexpr size_t lean_grouped_smem_bytes() { return lean_smem_bytes() + (size_t)kWarpsPerCta * kLeanFullWords * 4; }
 
 }  // namespace b2p

@@ -65,3 +65,61 @@ def finalize_host(agg: str, sum_a: np.ndarray, cnt_a: np.ndarray) -> np.ndarray:
         out = cnt_a.astype(np.float64)
     out[~nz] = 0.0
     return out
+
+
+def merge_partials(agg: str, val_t, cnt_t, mean_t=None, group=None):
+    """Host mirror of b2p_allreduce_partials_dev (same formulas, torch.distributed instead of the library's NCCL
+    communicator; used by the gloo tests): in-place merge of every rank's by-label partials.
+      sum / avg / count : val and cnt are added                       (commutativity.rs:85-113)
+      min / max         : groups absent on a rank (cnt == 0) are neutral (+inf / -inf), val is reduced with
+                          min / max, cnt is added, groups absent everywhere read 0.0 again
+      stddev / stdvar   : per-rank (cnt, mean, M2 = val) states; global mean from an all-reduce of cnt * mean,
+                          M2 = sum_r [M2_r + cnt_r (mean_r - mean)^2]  (commutativity.rs:158-191)"""
+    import torch
+    import torch.distributed as dist
+    cnt64 = cnt_t.to(torch.int64)
+    if agg in ("min", "max"):
+        neutral = float("inf") if agg == "min" else float("-inf")
+        val_t[cnt64 == 0] = neutral
+        dist.all_reduce(val_t, op=dist.ReduceOp.MIN if agg == "min" else dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(cnt64, op=dist.ReduceOp.SUM, group=group)
+        val_t[cnt64 == 0] = 0.0
+    elif agg in ("stddev", "stdvar"):
+        cnt_r = cnt64.clone()
+        wsum = cnt_r.to(torch.float64) * mean_t
+        dist.all_reduce(wsum, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(cnt64, op=dist.ReduceOp.SUM, group=group)
+        mg = torch.where(cnt64 > 0, wsum / cnt64.clamp_min(1).to(torch.float64), torch.zeros_like(wsum))
+        d = mean_t - mg
+        val_t.copy_(torch.where(cnt_r > 0, val_t + cnt_r.to(torch.float64) * d * d, torch.zeros_like(val_t)))
+        mean_t.copy_(mg)
+        dist.all_reduce(val_t, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.all_reduce(val_t, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(cnt64, op=dist.ReduceOp.SUM, group=group)
+    cnt_t.copy_(cnt64.to(cnt_t.dtype))
+    return val_t, cnt_t
+
+
+def partial_state_host(agg: str, vals: np.ndarray, valid: np.ndarray, gid: np.ndarray, n_groups: int):
+    """Host mirror of b2p_group_aggregate_partial_dev for stddev / stdvar: (M2, cnt, mean) per (group, step), Welford in
+    series order like the by-label kernel."""
+    S, T = vals.shape
+    Tw = valid.shape[1]
+    m2 = np.zeros((n_groups, T))
+    mean = np.zeros((n_groups, T))
+    cnt = np.zeros((n_groups, T), np.int64)
+    bits = ((valid[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(S, Tw * 32)[:, :T].astype(bool)
+    for s in range(S):
+        g = int(gid[s])
+        if g >= n_groups:
+            continue
+        k = np.flatnonzero(bits[s])
+        x = vals[s, k]
+        n1 = cnt[g, k] + 1.0
+        d1 = x - mean[g, k]
+        nm = d1 / n1 + mean[g, k]
+        m2[g, k] += d1 * (x - nm)
+        mean[g, k] = nm
+        cnt[g, k] += 1
+    return m2, cnt, mean

@@ -272,6 +272,9 @@ class Context:
                                                               n_rows, n_series, index, n_tiles, _ptr(out_sum),
                                                               _ptr(out_cnt)))
 
+    def allreduce_columns_dev(self, col_sum, col_cnt, n_cols):
+        self._check(self._L.b2p_allreduce_columns_dev(self._h, _ptr(col_sum), _ptr(col_cnt), n_cols))
+
     def group_finalize_dev(self, agg, val, cnt, n):
         aid = AGG_IDS[agg] if isinstance(agg, str) else int(agg)
         self._check(self._L.b2p_group_finalize_dev(self._h, aid, _ptr(val), _ptr(cnt), n))

@@ -212,6 +212,8 @@ B2P_API int b2p_comm_destroy(b2p_ctx* ctx);
  * cnt; MIN / MAX reduce val with min / max (groups absent on a rank are neutral) and add cnt; STDDEV / STDVAR merge
  * the (cnt, mean, M2 = val) states.  A context without communicator and n_ranks == 1 returns at once. */
 B2P_API int b2p_allreduce_partials_dev(b2p_ctx* ctx, int32_t agg, double* val, uint32_t* cnt, double* mean, uint64_t n);
+/* Wide avg_over_time (config 5): per-column (sum, count) of every rank added in place. */
+B2P_API int b2p_allreduce_columns_dev(b2p_ctx* ctx, double* sum, uint64_t* cnt, uint32_t n_cols);
 /* sum by (..)(fn(..)) over ALL ranks: this rank's fused partials, computed in n_tiles group ranges; each range's rows
  * of out_sum / out_cnt are all-reduced on a high-priority communication stream as soon as they are complete, while
  * the next range computes (kernel time of the last tile's all-reduce: b2p_last_kernel_ms(ctx, 4)).  On return

@@ -25,11 +25,38 @@ FN_IDS = {
 AGG_OPS = {"sum": 0, "avg": 1, "count": 2, "min": 3, "max": 4, "stddev": 5, "stdvar": 6}
 
 
+def _cpu_stamp() -> str:
+    """Identity of the host CPU (model + ISA flags): the oracle is compiled -march=native and travels with the
+    snapshot, so a library built on another CPU is rebuilt here before it is loaded."""
+    try:
+        model, flags = "", ""
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name") and not model:
+                    model = ln.split(":", 1)[1].strip()
+                elif ln.startswith("flags") and not flags:
+                    flags = " ".join(sorted(ln.split(":", 1)[1].split()))
+                if model and flags:
+                    break
+        import hashlib
+        return model + " " + hashlib.sha1(flags.encode()).hexdigest()
+    except OSError:
+        return "unknown"
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (oracle/Makefile).  Building the checker is not using it."""
     src = [os.path.join(_HERE, f) for f in ("promql_oracle.c", "promql_oracle.h", "Makefile")]
-    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
-        subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+    stamp_path = _SO + ".cpu"
+    stamp = _cpu_stamp()
+    try:
+        same_cpu = open(stamp_path).read() == stamp
+    except OSError:
+        same_cpu = False
+    if force or not same_cpu or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(["make", "-s", "-B", "-C", _HERE, "liboracle.so"])
+        with open(stamp_path, "w") as f:
+            f.write(stamp)
     return _SO
 
 

@@ -40,14 +40,40 @@ def _worker(rank, world, port, q):
     st, ct = torch.from_numpy(psum), torch.from_numpy(pcnt.astype(np.int64))
     D.allreduce_group_partials(st, ct)
     res = D.finalize_host("avg", st.numpy(), ct.numpy())
+    full_out, full_valid = orc.range_query(p, ts, val, sid, offsets)
+    worst = 0.0
+    ok_all = True
+    # min / max: groups missing on one rank must not poison the extreme; stddev / stdvar: (cnt, mean, M2) states merge
+    for agg in ("min", "max", "stddev", "stdvar"):
+        e_val, e_cnt = orc.group_aggregate(agg, full_out, full_valid, gid, G)
+        if agg in ("min", "max"):
+            pv, pc = orc.group_aggregate(agg, out, valid, gid[owned], G)
+            vt, ctt = torch.from_numpy(pv.copy()), torch.from_numpy(pc.astype(np.int64))
+            D.merge_partials(agg, vt, ctt)
+            got = vt.numpy()
+        else:
+            m2, pc, mean = D.partial_state_host(agg, out, valid, gid[owned], G)
+            vt, ctt, mt = torch.from_numpy(m2), torch.from_numpy(pc), torch.from_numpy(mean)
+            D.merge_partials(agg, vt, ctt, mt)
+            n = np.maximum(ctt.numpy(), 1)
+            got = vt.numpy() / n if agg == "stdvar" else np.sqrt(vt.numpy() / n)
+            got[ctt.numpy() == 0] = 0.0
+        ok_all = ok_all and bool((ctt.numpy() == e_cnt).all())
+        m = e_cnt > 0
+        rel_a = np.abs(got[m] - e_val[m]) / np.maximum(np.abs(e_val[m]), 1e-300)
+        # variance of near-constant samples cancels: compare absolutely against the scale of the data there
+        scale = np.abs(full_out).max()
+        bad = (rel_a > 1e-9) & (np.abs(got[m] - e_val[m]) > 1e-9 * scale)
+        ok_all = ok_all and not bool(bad.any())
+        if agg in ("min", "max"):
+            ok_all = ok_all and bool((got[m] == e_val[m]).all())   # extremes are exact
     if rank == 0:
-        full_out, full_valid = orc.range_query(p, ts, val, sid, offsets)
         e_avg, e_cnt = orc.group_aggregate("avg", full_out, full_valid, gid, G)
-        ok_cnt = bool((ct.numpy() == e_cnt).all())
+        ok_cnt = bool((ct.numpy() == e_cnt).all()) and ok_all
         rel = np.abs(res - e_avg) / np.maximum(np.abs(e_avg), 1e-300)
         q.put((ok_cnt, float(rel[e_cnt > 0].max()), int(owned.size)))
     else:
-        q.put((True, 0.0, int(owned.size)))
+        q.put((ok_all, 0.0, int(owned.size)))
     dist.barrier()
     dist.destroy_process_group()
 
