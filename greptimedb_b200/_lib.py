@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "b2p_group_index_create_dev", "b2p_group_index_destroy", "b2p_group_aggregate_indexed_dev",
     "b2p_range_group_sum_indexed_dev", "b2p_range_group_sum_fused", "b2p_group_aggregate_partial_dev",
     "b2p_comm_unique_id", "b2p_comm_init", "b2p_comm_destroy", "b2p_allreduce_partials_dev",
-    "b2p_range_group_sum_allreduce_dev", "b2p_allreduce_columns_dev",
+    "b2p_range_group_sum_allreduce_dev", "b2p_allreduce_columns_dev", "b2p_histogram_fold_dev", "b2p_range_histogram_fold",
     "b2p_column_reduce_dev", "b2p_range_eval", "b2p_range_udf", "b2p_instant_select", "b2p_group_aggregate",
     "b2p_histogram_quantile", "b2p_synth_fill_dev",
     "b2p_plan_range_create", "b2p_plan_set_instant", "b2p_plan_set_histogram_quantile", "b2p_plan_push_batch", "b2p_plan_execute", "b2p_plan_num_series", "b2p_plan_destroy",
@@ -86,6 +86,8 @@ def load() -> C.CDLL:
         "b2p_allreduce_partials_dev": (C.c_int, [vp, i32, vp, vp, vp, u64]),
         "b2p_range_group_sum_allreduce_dev": (C.c_int, [vp, P, vp, vp, vp, u64, u32, vp, i32, vp, vp]),
         "b2p_allreduce_columns_dev": (C.c_int, [vp, vp, vp, u32]),
+        "b2p_histogram_fold_dev": (C.c_int, [vp, dbl, vp, vp, vp, u32, vp, vp, u64, vp, vp]),
+        "b2p_range_histogram_fold": (C.c_int, [vp, P, vp, vp, vp, vp, u64, u32, dbl, vp, vp, vp, u32, vp, vp]),
         "b2p_histogram_quantile_dev": (C.c_int, [vp, dbl, vp, u32, vp, vp, u32, u64, vp, vp]),
         "b2p_column_reduce_dev": (C.c_int, [vp, vp, u32, u64, vp, vp]),
         "b2p_range_eval": (C.c_int, [vp, P, vp, vp, vp, vp, u64, u32, vp, vp, vp]),

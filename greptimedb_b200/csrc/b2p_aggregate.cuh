@@ -1,7 +1,7 @@
 // b2p_aggregate.cuh — kernels above the range functions:
 //   K3 group_aggregate_kernel  by-label aggregate (DataFusion AggregateExec planned by
 //                              prom_aggr_expr_to_plan, src/query/src/promql/planner.rs:334-452)
-//   K5 histogram_quantile_kernel  HistogramFold::evaluate_row (histogram_fold.rs:1046-1118)
+//   K5 histogram_fold_kernel   HistogramFold: fold_buf + safe mode + evaluate_row (histogram_fold.rs:754-1118)
 //   K6 column_reduce_*         per-column sum/count of a wide f64 table (config 5)
 #pragma once
 #include <cstdint>
@@ -62,10 +62,10 @@ __global__ void __launch_bounds__(256) group_aggregate_kernel(const GroupArgs a)
       if constexpr (AGG == B2P_AGG_SUM || AGG == B2P_AGG_AVG) {
         acc += x;
       } else if constexpr (AGG == B2P_AGG_COUNT) {
-      } else if constexpr (AGG == B2P_AGG_MIN) {
-        if (cnt == 0 || x < acc || (isnan(acc) && !isnan(x))) acc = x;
+      } else if constexpr (AGG == B2P_AGG_MIN) {  // f64::total_cmp order (arrow-rs / DataFusion min, max): +NaN is greatest
+        if (cnt == 0 || total_key(x) < total_key(acc)) acc = x;
       } else if constexpr (AGG == B2P_AGG_MAX) {
-        if (cnt == 0 || x > acc || (isnan(acc) && !isnan(x))) acc = x;
+        if (cnt == 0 || total_key(x) > total_key(acc)) acc = x;
       } else {  // Welford, population variance
         const double new_count = (double)cnt + 1.0;
         const double delta1 = x - mean;
@@ -187,127 +187,193 @@ __global__ void __launch_bounds__(256) group_offsets_kernel(const uint32_t* sort
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5.  One warp per (histogram, 32-step tile); lane = step.  Each lane walks the B cumulative
-// bucket counters of its (histogram, step) twice — once to get the (monotonised) total, once to
-// locate the bucket — reading rates[(h*B+b)*T + k], a coalesced 256-byte segment per bucket.
-// A row exists iff all B buckets are present at that step (the reference folds complete groups,
-// histogram_fold.rs:772-813).
+// K5 HistogramFold on the device (histogram_fold.rs:754-820 fold_buf, :834-981 safe mode, :1046-1118 evaluate_row).
+// A histogram is a list of bucket series ordered by their `le` bound (CSR hist_off / bucket_series / bucket_le, built
+// once per query from the labels); layouts may differ between histograms.  For every (histogram, eval step) the row
+// the reference folds consists of the buckets that HAVE a sample at that step (rows with a null rate were filtered
+// before the fold), in le order:
+//   no bucket present            -> no output row
+//   fewer than two, or the last present bound is not +Inf -> NaN   (safe mode, :930-944; evaluate_row :1048-1055)
+//   otherwise evaluate_row on the present (bound, counter) pairs.
+// One warp per (histogram, 32-step tile), lane = step: ONE pass over HBM — each bucket's 32-step segment is read once
+// (coalesced 256 bytes), counters are made finite and monotone on the way into shared memory ([slot][lane] columns,
+// conflict free; slot = rank among the present buckets of that step), then every lane bisects its own column.
+// Algorithmic traffic: 8 B x buckets + 1 bit x buckets read, 8 B + 1 bit written per (histogram, step).  Histograms
+// with more than kHistSmemBuckets buckets take the two-pass walk below (second pass from L2).
 // ---------------------------------------------------------------------------------------------
-struct HistArgs {
+struct HistFoldArgs {
   double phi;
-  const double* le;  // [B] bucket upper bounds, ascending, last = +Inf
-  uint32_t B;
-  const double* rates;
-  const uint32_t* valid;
+  const uint32_t* hist_off;       // [n_hist + 1] into bucket_series / bucket_le
+  const uint32_t* bucket_series;  // series id of every bucket, per histogram in ascending le order (NaN bounds last)
+  const double* bucket_le;        // parsed bound of every bucket (NaN when the label does not parse, :791-796)
   uint32_t n_hist;
+  const double* rates;            // [n_series x T]
+  const uint32_t* valid;          // [n_series x Tw]
   uint64_t T;
   uint32_t Tw;
-  double* out;
-  uint32_t* out_valid;
+  double* out;                    // [n_hist x T]
+  uint32_t* out_valid;            // [n_hist x Tw]
 };
 
-// The row evaluation of HistogramFold::evaluate_row (histogram_fold.rs:1046-1118) once the monotonised counters
-// c[0..B) of the row are known through `get(b)`, its total and the per-query bucket checks.
-template <class Get>
-__device__ __forceinline__ double histogram_row(const HistArgs& a, bool bucket_sorted, bool last_inf, double total_c, Get get) {
+constexpr int kHistWarps = 4;          // warps per CTA
+constexpr int kHistSmemBuckets = 64;   // rows with up to this many buckets keep their counters in shared memory
+
+// evaluate_row from the quantile checks on (histogram_fold.rs:1062-1118); n >= 2 present buckets whose last bound is
+// +Inf and whose bounds are non-decreasing; cnt(i) / le(i) give the i-th present bucket's monotonised counter / bound.
+template <class Cnt, class Le>
+__device__ __forceinline__ double histogram_row(double phi, uint32_t n, Cnt cnt, Le le) {
   const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
   const double kInf = __longlong_as_double(0x7ff0000000000000ll);
-  if (a.B <= 1) return kNaN;
-  if (!last_inf) return kNaN;  // Err("last bucket should be +Inf") -> unwrap_or(NaN), :806
-  if (a.phi < 0.0) return -kInf;
-  if (a.phi > 1.0) return kInf;
-  if (isnan(a.phi)) return kNaN;
-  if (!bucket_sorted) return kNaN;
-  const double expected_pos = total_c * a.phi;
-  // first bucket whose counter is >= expected_pos: the counters are non-decreasing, so bisect
-  uint32_t lo = 0, hi = a.B;  // answer in [lo, hi]; hi == B: none (cannot happen: c[B-1] = total >= pos for phi <= 1)
+  if (phi < 0.0) return -kInf;
+  if (phi > 1.0) return kInf;
+  if (isnan(phi)) return kNaN;
+  const double total = cnt(n - 1);
+  const double expected_pos = total * phi;
+  // first present bucket whose counter is >= expected_pos: the counters are non-decreasing, so bisect
+  uint32_t lo = 0, hi = n;
   while (lo < hi) {
     const uint32_t mid = (lo + hi) >> 1;
-    if (get(mid) < expected_pos) lo = mid + 1; else hi = mid;
+    if (cnt(mid) < expected_pos) lo = mid + 1; else hi = mid;
   }
   const uint32_t fit = lo;
-  if (fit >= a.B - 1) return a.le[a.B - 2];
-  const double upper_count = get(fit);
-  const double upper_bound = a.le[fit];
-  double lower_bound = fmin(a.le[0], 0.0), lower_count = 0.0;
+  if (fit >= n - 1) return le(n - 2);
+  const double upper_count = cnt(fit), upper_bound = le(fit);
+  double lower_bound = fmin(le(0), 0.0), lower_count = 0.0;
   if (fit > 0) {
-    lower_bound = a.le[fit - 1];
-    lower_count = get(fit - 1);
+    lower_bound = le(fit - 1);
+    lower_count = cnt(fit - 1);
   }
   if (fabs(upper_count - lower_count) < 1e-10) return kNaN;
   return lower_bound + (upper_bound - lower_bound) / (upper_count - lower_count) * (expected_pos - lower_count);
 }
 
-constexpr int kHistWarps = 4;          // warps per CTA of K5
-constexpr int kHistSmemBuckets = 64;   // rows with up to this many buckets keep their counters in shared memory
-
-// One pass over HBM: the warp reads the B rate segments of its (histogram, 32-step tile) once (coalesced 256 bytes per
-// bucket, eight requests in flight per lane), monotonises them on the way into shared memory ([bucket][lane], conflict
-// free), then every lane bisects its own column.  Algorithmic traffic: 8 B x B + B bits read, 8 B + 1 bit written per
-// (histogram, step).  Rows with more than kHistSmemBuckets buckets re-read the segments for the bisection (L2 hits).
-__global__ void __launch_bounds__(kHistWarps * 32) histogram_quantile_kernel(const HistArgs a) {
+__global__ void __launch_bounds__(kHistWarps * 32) histogram_fold_kernel(const HistFoldArgs a) {
   extern __shared__ __align__(16) unsigned char hist_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* col = reinterpret_cast<double*>(hist_smem) + (size_t)warp * kHistSmemBuckets * 32 + lane;  // col[b * 32]
+  double* col = reinterpret_cast<double*>(hist_smem) + (size_t)warp * kHistSmemBuckets * 32 + lane;  // col[slot * 32]
+  unsigned char* idx = hist_smem + (size_t)kHistWarps * kHistSmemBuckets * 32 * 8 + (size_t)warp * kHistSmemBuckets * 32 + lane;
+  const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
   const uint64_t tiles = (a.T + 31) / 32;
   const uint64_t total = (uint64_t)a.n_hist * tiles;
-  const bool in_smem = a.B <= (uint32_t)kHistSmemBuckets;
-  // bucket checks are identical for every row (histogram_fold.rs:1047-1073)
-  bool bucket_sorted = true;
-  for (uint32_t b = 0; b + 1 < a.B; ++b) bucket_sorted &= (a.le[b] <= a.le[b + 1]);
-  const bool last_inf = a.B > 0 && !isfinite(a.le[a.B - 1]);
   for (uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total;
        w += ((uint64_t)gridDim.x * blockDim.x) >> 5) {
     const uint32_t h = (uint32_t)(w / tiles);
     const uint64_t tile = w - (uint64_t)h * tiles;
     const uint64_t k = tile * 32 + lane;
     const bool in = k < a.T;
-    const size_t s0 = (size_t)h * a.B;
-    // a row exists iff all B buckets are present at that step: lanes fetch the validity words of 32 buckets at a time
-    uint32_t all = 0xffffffffu;
-    for (uint32_t b0 = 0; b0 < a.B; b0 += 32) {
-      const uint32_t wv = (b0 + lane < a.B) ? a.valid[(s0 + b0 + lane) * a.Tw + tile] : 0xffffffffu;
-      all &= __reduce_and_sync(0xffffffffu, wv);
-    }
-    const double* seg = a.rates + s0 * a.T + (in ? k : 0);
-    double prev = 0.0;
-    for (uint32_t b0 = 0; b0 < a.B; b0 += 8) {
-      double v[8];
+    const uint32_t o = a.hist_off[h], nb = a.hist_off[h + 1] - o;
+    const uint32_t* bs = a.bucket_series + o;
+    const double* ble = a.bucket_le + o;
+    uint32_t n = 0;          // present buckets of this lane's step
+    double prev = 0.0;       // monotonised counter of the previous present bucket
+    double last_le = kNaN, prev_le = -__longlong_as_double(0x7ff0000000000000ll);
+    bool sorted = true;      // bucket.windows(2).all(|w| w[0] <= w[1]) over the present bounds
+    bool ok = false;
+    double r = 0.0;
+    if (nb <= (uint32_t)kHistSmemBuckets) {
+      for (uint32_t b0 = 0; b0 < nb; b0 += 8) {
+        double v[8];
+        uint32_t wd[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = (b0 + u < a.B && in) ? __ldcs(seg + (size_t)(b0 + u) * a.T) : 0.0;
+        for (int u = 0; u < 8; ++u) {
+          const bool has = b0 + u < nb;
+          const uint32_t s = has ? bs[b0 + u] : 0u;
+          wd[u] = has ? a.valid[(size_t)s * a.Tw + tile] : 0u;
+          v[u] = (has && in && ((wd[u] >> lane) & 1u)) ? __ldcs(a.rates + (size_t)s * a.T + k) : 0.0;
+        }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (b0 + u < a.B) {
-          double c = isfinite(v[u]) ? v[u] : prev;  // non-finite -> previous, decreasing -> previous (:1074-1092)
-          if (b0 + u > 0 && c < prev) c = prev;
-          prev = c;
-          if (in_smem) col[(b0 + u) * 32] = c;
+        for (int u = 0; u < 8; ++u) {
+          if (b0 + u < nb && in && ((wd[u] >> lane) & 1u)) {
+            double c = isfinite(v[u]) ? v[u] : prev;   // non-finite -> previous, decreasing -> previous (:1074-1092)
+            if (n > 0 && c < prev) c = prev;
+            prev = c;
+            col[n * 32] = c;
+            idx[n * 32] = (unsigned char)(b0 + u);
+            const double l = ble[b0 + u];
+            sorted = sorted && (n == 0 || prev_le <= l);
+            prev_le = l;
+            last_le = l;
+            ++n;
+          }
+        }
+      }
+      ok = n > 0;
+      if (ok) {
+        const bool has_inf = !(last_le < __longlong_as_double(0x7ff0000000000000ll)) && !isnan(last_le) && last_le > 0.0;
+        if (n < 2 || !has_inf) r = kNaN;
+        else if (!sorted && !(a.phi < 0.0) && !(a.phi > 1.0)) r = kNaN;
+        else r = histogram_row(a.phi, n, [&](uint32_t i) { return col[i * 32]; }, [&](uint32_t i) { return ble[idx[i * 32]]; });
+      }
+    } else if (in) {
+      // wide histogram: walk the buckets twice (presence, total and checks; then the linear search of the reference)
+      for (uint32_t b = 0; b < nb; ++b) {
+        const uint32_t s = bs[b];
+        if (!((a.valid[(size_t)s * a.Tw + tile] >> lane) & 1u)) continue;
+        const double x = a.rates[(size_t)s * a.T + k];
+        double c = isfinite(x) ? x : prev;
+        if (n > 0 && c < prev) c = prev;
+        prev = c;
+        const double l = ble[b];
+        sorted = sorted && (n == 0 || prev_le <= l);
+        prev_le = l;
+        last_le = l;
+        ++n;
+      }
+      ok = n > 0;
+      if (ok) {
+        const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+        const bool has_inf = last_le == kInf;
+        if (n < 2 || !has_inf) r = kNaN;
+        else if (a.phi < 0.0) r = -kInf;
+        else if (a.phi > 1.0) r = kInf;
+        else if (isnan(a.phi) || !sorted) r = kNaN;
+        else {
+          const double expected_pos = prev * a.phi;  // prev = total after the first walk
+          uint32_t i = 0, fit = n;
+          double run = 0.0, run_le = 0.0, le0 = 0.0, le_nm2 = 0.0, lc = 0.0, lb = 0.0, uc = 0.0, ub = 0.0;
+          for (uint32_t b = 0; b < nb; ++b) {
+            const uint32_t s = bs[b];
+            if (!((a.valid[(size_t)s * a.Tw + tile] >> lane) & 1u)) continue;
+            const double x = a.rates[(size_t)s * a.T + k];
+            double c = isfinite(x) ? x : run;
+            if (i > 0 && c < run) c = run;
+            const double l = ble[b];
+            if (i == 0) le0 = l;
+            if (i == n - 2) le_nm2 = l;
+            if (fit == n && !(c < expected_pos)) {  // the reference's linear search stops here
+              fit = i;
+              uc = c;
+              ub = l;
+              lc = i > 0 ? run : 0.0;
+              lb = i > 0 ? run_le : fmin(le0, 0.0);
+            }
+            run = c;
+            run_le = l;
+            ++i;
+          }
+          if (fit >= n - 1) r = le_nm2;
+          else if (fabs(uc - lc) < 1e-10) r = kNaN;
+          else r = lb + (ub - lb) / (uc - lc) * (expected_pos - lc);
         }
       }
     }
-    const bool ok = in && ((all >> lane) & 1u);
-    double r = 0.0;
-    if (ok) {
-      if (in_smem) {
-        r = histogram_row(a, bucket_sorted, last_inf, prev, [&](uint32_t b) { return col[b * 32]; });
-      } else {
-        // counters of bucket b on demand: the running maximum needs the buckets before it — walk (rare, wide rows)
-        r = histogram_row(a, bucket_sorted, last_inf, prev, [&](uint32_t b) {
-          double p = 0.0;
-          for (uint32_t q = 0; q <= b; ++q) {
-            const double x = seg[(size_t)q * a.T];
-            double c = isfinite(x) ? x : p;
-            if (q > 0 && c < p) c = p;
-            p = c;
-          }
-          return p;
-        });
-      }
-    }
-    if (in) a.out[(size_t)h * a.T + k] = r;
+    if (in) a.out[(size_t)h * a.T + k] = ok ? r : 0.0;
     const uint32_t word = __ballot_sync(0xffffffffu, ok);
     if (lane == 0) a.out_valid[(size_t)h * a.Tw + tile] = word;
   }
+}
+
+// uniform layout (bucket b of histogram h = series h * B + b, shared bounds le[B]) -> the CSR the fold kernel takes
+__global__ void __launch_bounds__(256) histogram_uniform_index_kernel(const double* le, uint32_t B, uint32_t n_hist,
+                                                                      uint32_t* hist_off, uint32_t* bucket_series,
+                                                                      double* bucket_le) {
+  const uint64_t n = (uint64_t)n_hist * B;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    bucket_series[i] = (uint32_t)i;
+    bucket_le[i] = le[i % B];
+    if (i % B == 0) hist_off[i / B] = (uint32_t)i;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) hist_off[n_hist] = (uint32_t)n;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -198,6 +198,8 @@ struct b2p_ctx {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
   DevBuf p_ts[2], p_val[2], p_sid[2], p_off[2], p_out[2], p_valid[2], p_status;
+  // uniform histogram layout -> fold index (b2p_histogram_quantile_dev)
+  DevBuf hq_off, hq_series, hq_les;
   // group aggregate scratch
   DevBuf g_keys_in, g_keys_out, g_vals_in, g_vals_out, g_goff, g_tmp;
   // column reduce scratch
@@ -577,7 +579,7 @@ void b2p_destroy(b2p_ctx* c) {
   if (c->ev_comm_in) cudaEventDestroy(c->ev_comm_in);
   if (c->ev_comm_done) cudaEventDestroy(c->ev_comm_done);
   if (c->ev_comm_go) cudaEventDestroy(c->ev_comm_go);
-  for (DevBuf* b : {&c->w_skip, &c->b_skip, &c->slow_skip, &c->m_tmp0, &c->m_tmp1}) b->release();
+  for (DevBuf* b : {&c->w_skip, &c->b_skip, &c->slow_skip, &c->m_tmp0, &c->m_tmp1, &c->hq_off, &c->hq_series, &c->hq_les}) b->release();
   for (DevBuf* b : {&c->slow_list, &c->w_list, &c->b_list, &c->arena_ts, &c->arena_val, &c->win_scratch, &c->h_ts, &c->h_val, &c->h_sid,
                     &c->h_off, &c->h_out, &c->h_valid, &c->h_aux0, &c->h_aux1, &c->h_aux2, &c->h_aux3,
                     &c->g_keys_in, &c->g_keys_out, &c->g_vals_in, &c->g_vals_out, &c->g_goff, &c->g_tmp, &c->c_psum,
@@ -1327,6 +1329,37 @@ int b2p_group_finalize_dev(b2p_ctx* c, int32_t agg, double* val, const uint32_t*
   return B2P_OK;
 }
 
+// HistogramFold over an explicit (histogram -> buckets in le order) index; every pointer is a device pointer.
+int b2p_histogram_fold_dev(b2p_ctx* c, double phi, const uint32_t* hist_off, const uint32_t* bucket_series,
+                           const double* bucket_le, uint32_t n_hist, const double* rates, const uint32_t* valid_words,
+                           uint64_t T, double* out, uint32_t* out_valid_words) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  if (n_hist == 0 || T == 0) return B2P_OK;
+  if (!hist_off || !bucket_series || !bucket_le || !rates || !valid_words || !out || !out_valid_words)
+    return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  HistFoldArgs a{};
+  a.phi = phi; a.hist_off = hist_off; a.bucket_series = bucket_series; a.bucket_le = bucket_le; a.n_hist = n_hist;
+  a.rates = rates; a.valid = valid_words; a.T = T; a.Tw = (uint32_t)((T + 31) / 32); a.out = out; a.out_valid = out_valid_words;
+  const uint64_t warps = (uint64_t)n_hist * ((T + 31) / 32);
+  uint64_t blocks = (warps + kHistWarps - 1) / kHistWarps;
+  const uint64_t cap = (uint64_t)c->num_sms * 3;  // 72 KB of counters + slots per CTA: three CTAs per SM
+  if (blocks > cap) blocks = cap;
+  constexpr size_t smem = (size_t)kHistWarps * kHistSmemBuckets * 32 * (8 + 1);
+  static bool attr_set[16] = {};
+  if (!attr_set[c->device & 15]) {
+    CU(cudaFuncSetAttribute(histogram_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[c->device & 15] = true;
+  }
+  stage_begin(c, 3);
+  histogram_fold_kernel<<<(unsigned)blocks, kHistWarps * 32, smem, c->stream>>>(a);
+  c->launches++;
+  stage_end(c, 3);
+  CU(cudaGetLastError());
+  return B2P_OK;
+}
+
+// Uniform layout: bucket b of histogram h is series h * n_buckets + b and every histogram has the bounds le[].
 int b2p_histogram_quantile_dev(b2p_ctx* c, double phi, const double* le, uint32_t n_buckets, const double* rates,
                                const uint32_t* valid_words, uint32_t n_hist, uint64_t T, double* out,
                                uint32_t* out_valid_words) {
@@ -1334,26 +1367,22 @@ int b2p_histogram_quantile_dev(b2p_ctx* c, double phi, const double* le, uint32_
   if (n_hist == 0 || T == 0) return B2P_OK;
   if (!le || !rates || !valid_words || !out || !out_valid_words || n_buckets == 0)
     return fail(B2P_E_INVALID, "NULL argument");
+  if ((uint64_t)n_hist * n_buckets > 0xffffffffull) return fail(B2P_E_TOO_LARGE, "more than 2^32 bucket series");
   DeviceGuard g(c->device);
-  HistArgs a{};
-  a.phi = phi; a.le = le; a.B = n_buckets; a.rates = rates; a.valid = valid_words; a.n_hist = n_hist; a.T = T;
-  a.Tw = (uint32_t)((T + 31) / 32); a.out = out; a.out_valid = out_valid_words;
-  const uint64_t warps = (uint64_t)n_hist * ((T + 31) / 32);
-  uint64_t blocks = (warps + kHistWarps - 1) / kHistWarps;
-  const uint64_t cap = (uint64_t)c->num_sms * 3;  // 64 KB of counters per CTA: three CTAs per SM
-  if (blocks > cap) blocks = cap;
-  constexpr size_t smem = (size_t)kHistWarps * kHistSmemBuckets * 32 * 8;
-  static bool attr_set[16] = {};
-  if (!attr_set[c->device & 15]) {
-    CU(cudaFuncSetAttribute(histogram_quantile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[c->device & 15] = true;
+  int rc;
+  const size_t nb = (size_t)n_hist * n_buckets;
+  {  // the fold index of the uniform layout (12 B per bucket series, rebuilt per call: microseconds)
+    if ((rc = c->hq_off.ensure(((size_t)n_hist + 1) * 4)) || (rc = c->hq_series.ensure(nb * 4)) || (rc = c->hq_les.ensure(nb * 8)))
+      return rc;
+    uint64_t blocks = (nb + 255) / 256;
+    if (blocks > (uint64_t)c->num_sms * 16) blocks = (uint64_t)c->num_sms * 16;
+    histogram_uniform_index_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(le, n_buckets, n_hist, c->hq_off.as<uint32_t>(),
+                                                                            c->hq_series.as<uint32_t>(), c->hq_les.as<double>());
+    c->launches++;
+    CU(cudaGetLastError());
   }
-  stage_begin(c, 3);
-  histogram_quantile_kernel<<<(unsigned)blocks, kHistWarps * 32, smem, c->stream>>>(a);
-  c->launches++;
-  stage_end(c, 3);
-  CU(cudaGetLastError());
-  return B2P_OK;
+  return b2p_histogram_fold_dev(c, phi, c->hq_off.as<uint32_t>(), c->hq_series.as<uint32_t>(), c->hq_les.as<double>(), n_hist,
+                                rates, valid_words, T, out, out_valid_words);
 }
 
 int b2p_column_reduce_dev(b2p_ctx* c, const double* const* cols, uint32_t n_cols, uint64_t n_rows, double* out_sum,
@@ -1718,6 +1747,58 @@ int b2p_histogram_quantile(b2p_ctx* c, double phi, const double* le, uint32_t n_
     return rc;
   CU(cudaMemcpyAsync(out, c->h_out.p, (size_t)n_hist * T * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(out_valid_words, c->h_valid.p, (size_t)n_hist * Tw * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B2P_OK;
+}
+
+// histogram_quantile(phi, fn(bucket_series[range])) from host buffers to host rows without the dense [n_series x T]
+// matrix ever leaving the device: H2D of the samples, series offsets, the range function into context scratch, the
+// HistogramFold over the caller's (histogram -> buckets in le order) index, D2H of [n_hist x T] only.
+int b2p_range_histogram_fold(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, const double* val,
+                             const uint32_t* sid, const uint64_t* offsets_host, uint64_t n_rows, uint32_t n_series,
+                             double phi, const uint32_t* hist_off, const uint32_t* bucket_series, const double* bucket_le,
+                             uint32_t n_hist, double* out, uint32_t* out_valid_words) {
+  if (!c) return fail(B2P_E_INVALID, "ctx is NULL");
+  int64_t T = 0;
+  int rc = check_grid(p, n_series, &T);
+  if (rc) return rc;
+  if (n_hist == 0 || T == 0) return B2P_OK;
+  if (!sid && !offsets_host) return fail(B2P_E_INVALID, "need sid or offsets_host");
+  if (!hist_off || !bucket_series || !bucket_le || !out || !out_valid_words || ((!ts || !val) && n_rows))
+    return fail(B2P_E_INVALID, "NULL argument");
+  DeviceGuard g(c->device);
+  if (!c->pending.empty() && (rc = b2p_sync(c))) return rc;
+  const uint32_t Tw = (uint32_t)((T + 31) / 32);
+  const size_t rows = n_rows ? n_rows : 1;
+  const size_t nb = hist_off[n_hist];
+  if ((rc = c->h_ts.ensure(rows * 8 + 16)) || (rc = c->h_val.ensure(rows * 8 + 16)) ||
+      (rc = c->h_off.ensure(((size_t)n_series + 1) * 8)) || (rc = c->h_out.ensure((size_t)n_series * (size_t)T * 8)) ||
+      (rc = c->h_valid.ensure((size_t)n_series * Tw * 4)) || (rc = c->hq_off.ensure(((size_t)n_hist + 1) * 4)) ||
+      (rc = c->hq_series.ensure((nb ? nb : 1) * 4)) || (rc = c->hq_les.ensure((nb ? nb : 1) * 8)) ||
+      (rc = c->h_aux2.ensure((size_t)n_hist * (size_t)T * 8)) || (rc = c->h_aux3.ensure((size_t)n_hist * Tw * 4)))
+    return rc;
+  CU(cudaMemcpyAsync(c->h_ts.p, ts, n_rows * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->h_val.p, val, n_rows * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->hq_off.p, hist_off, ((size_t)n_hist + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->hq_series.p, bucket_series, nb * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->hq_les.p, bucket_le, nb * 8, cudaMemcpyHostToDevice, c->stream));
+  if (offsets_host) {
+    CU(cudaMemcpyAsync(c->h_off.p, offsets_host, ((size_t)n_series + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    if ((rc = c->h_sid.ensure(rows * 4 + 16))) return rc;
+    CU(cudaMemcpyAsync(c->h_sid.p, sid, n_rows * 4, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = series_offsets_impl(c, c->h_sid.as<uint32_t>(), n_rows, n_series, 0u, c->h_off.as<uint64_t>()))) return rc;
+  }
+  if ((rc = b2p_range_eval_dev(c, p, c->h_ts.as<int64_t>(), c->h_val.as<double>(), c->h_off.as<uint64_t>(), n_rows, n_series,
+                               c->h_out.as<double>(), c->h_valid.as<uint32_t>())))
+    return rc;
+  if ((rc = b2p_sync(c))) return rc;  // slow-path fix-ups land before the fold reads
+  if ((rc = b2p_histogram_fold_dev(c, phi, c->hq_off.as<uint32_t>(), c->hq_series.as<uint32_t>(), c->hq_les.as<double>(), n_hist,
+                                   c->h_out.as<double>(), c->h_valid.as<uint32_t>(), (uint64_t)T, c->h_aux2.as<double>(),
+                                   c->h_aux3.as<uint32_t>())))
+    return rc;
+  CU(cudaMemcpyAsync(out, c->h_aux2.p, (size_t)n_hist * (size_t)T * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(out_valid_words, c->h_aux3.p, (size_t)n_hist * Tw * 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return B2P_OK;
 }

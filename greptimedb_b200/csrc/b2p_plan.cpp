@@ -3,10 +3,14 @@
 #include "b2p_plan.hpp"
 
 #include <algorithm>
+#include <cctype>
+#include <charconv>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <numeric>
+#include <unordered_map>
 
 namespace b2p {
 
@@ -77,6 +81,57 @@ int function_id_from_name(const std::string& n) {
     if (n == f.name) return f.id;
   return -1;
 }
+// str::parse::<f64>() of Rust's std for a label value: optional sign, decimal digits with optional fraction and
+// exponent, or inf / infinity / nan in any case — nothing else (no surrounding white space, no hex floats, no locale
+// decimal comma: strtod would accept those).  Anything that does not parse is NaN (histogram_fold.rs:791-796).
+double parse_f64_like_rust(const std::string& v) {
+  const double nan = std::nan("");
+  if (v.empty()) return nan;
+  size_t i = 0;
+  bool neg = false;
+  if (v[0] == '+' || v[0] == '-') {
+    neg = v[0] == '-';
+    i = 1;
+  }
+  if (i >= v.size()) return nan;
+  auto ieq = [&](const char* w) {
+    size_t n = std::strlen(w);
+    if (v.size() - i != n) return false;
+    for (size_t k = 0; k < n; ++k)
+      if (std::tolower((unsigned char)v[i + k]) != w[k]) return false;
+    return true;
+  };
+  if (ieq("inf") || ieq("infinity")) return neg ? -HUGE_VAL : HUGE_VAL;
+  if (ieq("nan")) return nan;
+  bool digits = false, dot = false, exp = false;
+  for (size_t k = i; k < v.size(); ++k) {
+    const char ch = v[k];
+    if (ch >= '0' && ch <= '9') {
+      digits = true;
+    } else if (ch == '.' && !dot && !exp) {
+      dot = true;
+    } else if ((ch == 'e' || ch == 'E') && digits && !exp) {
+      exp = true;
+      if (k + 1 < v.size() && (v[k + 1] == '+' || v[k + 1] == '-')) ++k;
+      if (k + 1 >= v.size()) return nan;  // exponent without digits
+      digits = true;
+      for (size_t q = k + 1; q < v.size(); ++q)
+        if (v[q] < '0' || v[q] > '9') return nan;
+      break;
+    } else {
+      return nan;
+    }
+  }
+  if (!digits) return nan;
+  double out = 0.0;
+  const auto r = std::from_chars(v.data() + i, v.data() + v.size(), out, std::chars_format::general);
+  if (r.ec != std::errc() || r.ptr != v.data() + v.size()) {
+    if (r.ec == std::errc::result_out_of_range) out = HUGE_VAL;  // Rust saturates to inf (and to 0 on underflow)
+    else return nan;
+  }
+  return neg ? -out : out;
+}
+
 int aggregate_id_from_name(const std::string& n) {
   for (const auto& f : kAggs)
     if (n == f.name) return f.id;
@@ -257,10 +312,11 @@ void PromRangePlan::execute(ArrowArray* out, ArrowSchema* out_schema) {
   const int64_t T = b2p_num_steps(p.start, p.end, p.interval);
   const uint32_t S = (uint32_t)num_series_;
   const uint32_t Tw = (uint32_t)((T + 31) / 32);
-  std::vector<double> dense((size_t)S * (size_t)T);
-  std::vector<uint32_t> valid((size_t)S * Tw);
+  const bool fold_on_device = args_.histogram && fn_id_ >= 0;  // the dense matrix then never reaches the host
+  std::vector<double> dense(fold_on_device ? 0 : (size_t)S * (size_t)T);
+  std::vector<uint32_t> valid(fold_on_device ? 0 : (size_t)S * Tw);
   std::vector<int64_t> eval_ts((size_t)T);
-  if (S > 0 && T > 0) {
+  if (S > 0 && T > 0 && !(args_.histogram && fn_id_ >= 0)) {
     int rc;
     if (fn_id_ >= 0) {
       rc = b2p_range_eval(ctx_, &p, ts_.data(), val_.data(), sid_.data(), nullptr, ts_.size(), S, dense.data(),
@@ -293,48 +349,64 @@ void PromRangePlan::execute(ArrowArray* out, ArrowSchema* out_schema) {
     if (key_is_id_) throw PlanError(ErrorKind::Plan, "HistogramFold needs the le tag column, not a tsid key");
     const size_t le_idx = (size_t)(std::find(args_.tag_columns.begin(), args_.tag_columns.end(), args_.le_column) -
                                    args_.tag_columns.begin());
-    std::map<std::vector<std::string>, std::vector<std::pair<double, uint32_t>>> hist;  // key -> (le, series)
+    // histogram id of every series (hash of the tag tuple without le; ids in first-appearance order), its bound
+    std::unordered_map<std::string, uint32_t> hist_ids;
+    std::vector<std::vector<std::string>> hist_keys;
+    std::vector<uint32_t> hid(S);
+    std::vector<double> sle(S);
+    std::string flat;
     for (uint32_t s = 0; s < S; ++s) {
-      std::vector<std::string> key;
+      flat.clear();
       for (size_t t = 0; t < args_.tag_columns.size(); ++t)
-        if (t != le_idx) key.push_back(tags_.utf8[t][s]);
-      const std::string& le_s = tags_.utf8[le_idx][s];
-      char* endp = nullptr;
-      double le = std::strtod(le_s.c_str(), &endp);  // le.parse::<f64>().unwrap_or(NaN), histogram_fold.rs:791-796
-      if (endp == le_s.c_str() || *endp != 0) le = std::nan("");
-      hist[key].push_back({le, s});
-    }
-    std::vector<double> le_bounds;
-    std::vector<uint32_t> order;  // series in (histogram, bucket) order
-    for (auto& kv : hist) {
-      auto& b = kv.second;
-      std::stable_sort(b.begin(), b.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
-      if (le_bounds.empty()) {
-        for (auto& e : b) le_bounds.push_back(e.first);
-      } else {
-        bool same = b.size() == le_bounds.size();
-        for (size_t i = 0; same && i < b.size(); ++i)
-          same = (b[i].first == le_bounds[i]) || (std::isnan(b[i].first) && std::isnan(le_bounds[i]));
-        if (!same)
-          throw PlanError(ErrorKind::Execution, "HistogramFold: histograms with different bucket layouts (the reference's "
-                                                "safe mode, histogram_fold.rs:834-846) are not supported by the GPU node");
+        if (t != le_idx) {
+          flat += tags_.utf8[t][s];
+          flat.push_back('\x1f');
+        }
+      auto it = hist_ids.find(flat);
+      if (it == hist_ids.end()) {
+        it = hist_ids.emplace(flat, (uint32_t)hist_keys.size()).first;
+        std::vector<std::string> key;
+        for (size_t t = 0; t < args_.tag_columns.size(); ++t)
+          if (t != le_idx) key.push_back(tags_.utf8[t][s]);
+        hist_keys.push_back(std::move(key));
       }
-      for (auto& e : b) order.push_back(e.second);
+      hid[s] = it->second;
+      sle[s] = parse_f64_like_rust(tags_.utf8[le_idx][s]);  // le.parse::<f64>().unwrap_or(NaN), histogram_fold.rs:791-796
     }
-    const uint32_t B = (uint32_t)le_bounds.size();
-    const uint32_t H = (uint32_t)hist.size();
-    std::vector<double> hr((size_t)H * B * (size_t)T);
-    std::vector<uint32_t> hv((size_t)H * B * Tw);
-    for (size_t i = 0; i < order.size(); ++i) {
-      std::memcpy(&hr[i * (size_t)T], &dense[(size_t)order[i] * (size_t)T], (size_t)T * 8);
-      std::memcpy(&hv[i * Tw], &valid[(size_t)order[i] * Tw], (size_t)Tw * 4);
+    const uint32_t H = (uint32_t)hist_keys.size();
+    // output order = the reference's: rows sorted by the remaining tags (std::map order of the old implementation)
+    std::vector<uint32_t> hist_order(H);
+    for (uint32_t h = 0; h < H; ++h) hist_order[h] = h;
+    std::sort(hist_order.begin(), hist_order.end(), [&](uint32_t x, uint32_t y) { return hist_keys[x] < hist_keys[y]; });
+    std::vector<uint32_t> rank(H);
+    for (uint32_t r = 0; r < H; ++r) rank[hist_order[r]] = r;
+    // buckets of every histogram in ascending le order, NaN bounds last, ties in scan order (a strict weak ordering)
+    std::vector<uint32_t> bucket_series(S);
+    for (uint32_t s = 0; s < S; ++s) bucket_series[s] = s;
+    std::stable_sort(bucket_series.begin(), bucket_series.end(), [&](uint32_t x, uint32_t y) {
+      if (rank[hid[x]] != rank[hid[y]]) return rank[hid[x]] < rank[hid[y]];
+      const bool nx = std::isnan(sle[x]), ny = std::isnan(sle[y]);
+      if (nx != ny) return ny;
+      return !nx && sle[x] < sle[y];
+    });
+    std::vector<uint32_t> hist_off(H + 1, 0);
+    std::vector<double> bucket_le(S);
+    for (uint32_t i = 0; i < S; ++i) {
+      bucket_le[i] = sle[bucket_series[i]];
+      hist_off[rank[hid[bucket_series[i]]] + 1]++;
     }
+    for (uint32_t h = 0; h < H; ++h) hist_off[h + 1] += hist_off[h];
     std::vector<double> hq((size_t)H * (size_t)T);
     std::vector<uint32_t> hqv((size_t)H * Tw);
-    if (H > 0 && B > 0 && T > 0) {
-      const int rc = b2p_histogram_quantile(ctx_, args_.quantile, le_bounds.data(), B, hr.data(), hv.data(), H,
-                                            (uint64_t)T, hq.data(), hqv.data());
+    if (H > 0 && T > 0) {
+      if (fn_id_ < 0) throw PlanError(ErrorKind::Plan, "HistogramFold over an instant selector is not supported by this node");
+      const int rc = b2p_range_histogram_fold(ctx_, &p, ts_.data(), val_.data(), sid_.data(), nullptr, ts_.size(), S,
+                                              args_.quantile, hist_off.data(), bucket_series.data(), bucket_le.data(), H,
+                                              hq.data(), hqv.data());
+      if (rc == B2P_E_INVALID || rc == B2P_E_TOO_LARGE) throw PlanError(ErrorKind::Plan, b2p_last_error());
+      if (rc == B2P_E_UNSORTED) throw PlanError(ErrorKind::Internal, b2p_last_error());
       if (rc != B2P_OK) throw PlanError(ErrorKind::Execution, b2p_last_error());
+      for (int64_t k = 0; k < T; ++k) eval_ts[(size_t)k] = p.start + k * p.interval;
     }
     OwnedColumn* c_ts = add_col(args_.time_index, "tsm:");
     OwnedColumn* c_val = add_col(value_name, "g");
@@ -344,19 +416,18 @@ void PromRangePlan::execute(ArrowArray* out, ArrowSchema* out_schema) {
         c_tags.push_back(add_col(args_.tag_columns[t], "u"));
         c_tags.back()->offsets.push_back(0);
       }
-    uint32_t h = 0;
-    for (auto& kv : hist) {
+    for (uint32_t h = 0; h < H; ++h) {  // rows of histogram hist_order[h] (tag-sorted), one per eval step with a row
+      const std::vector<std::string>& key = hist_keys[hist_order[h]];
       for (int64_t k = 0; k < T; ++k) {
         if (!((hqv[(size_t)h * Tw + (size_t)(k >> 5)] >> (k & 31)) & 1u)) continue;
         c_ts->i64.push_back(eval_ts[(size_t)k]);
         c_val->f64.push_back(hq[(size_t)h * (size_t)T + (size_t)k]);
         for (size_t t = 0; t < c_tags.size(); ++t) {
-          c_tags[t]->chars += kv.first[t];
+          c_tags[t]->chars += key[t];
           c_tags[t]->offsets.push_back((int32_t)c_tags[t]->chars.size());
         }
         ++n_out;
       }
-      ++h;
     }
   } else if (agg_id_ < 0) {
     // rows of Filter(prom_fn IS NOT NULL): {time_index (eval ts), prom_fn(...), tags...}, series-major order

@@ -283,6 +283,11 @@ class Context:
         self._check(self._L.b2p_histogram_quantile_dev(self._h, float(phi), _ptr(le), n_buckets, _ptr(rates),
                                                        _ptr(valid), n_hist, T, _ptr(out), _ptr(out_valid)))
 
+    def histogram_fold_dev(self, phi, hist_off, bucket_series, bucket_le, n_hist, rates, valid, T, out, out_valid):
+        self._check(self._L.b2p_histogram_fold_dev(self._h, float(phi), _ptr(hist_off), _ptr(bucket_series),
+                                                   _ptr(bucket_le), n_hist, _ptr(rates), _ptr(valid), T, _ptr(out),
+                                                   _ptr(out_valid)))
+
     def column_reduce_dev(self, col_ptrs, n_cols, n_rows, out_sum, out_cnt):
         self._check(self._L.b2p_column_reduce_dev(self._h, _ptr(col_ptrs), n_cols, n_rows, _ptr(out_sum), _ptr(out_cnt)))
 

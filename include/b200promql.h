@@ -226,6 +226,14 @@ B2P_API int b2p_range_group_sum_allreduce_dev(b2p_ctx* ctx, const b2p_range_para
 B2P_API int b2p_histogram_quantile_dev(b2p_ctx* ctx, double phi, const double* le, uint32_t n_buckets,
                                const double* rates, const uint32_t* valid_words, uint32_t n_hist, uint64_t T,
                                double* out, uint32_t* out_valid_words);
+/* HistogramFold over an explicit index (device pointers): histogram h owns buckets hist_off[h] .. hist_off[h+1] of
+ * bucket_series / bucket_le, in ascending le order (NaN bounds last); layouts may differ between histograms.  Per
+ * (histogram, step) the buckets that have a sample at that step are folded like the reference's safe mode
+ * (histogram_fold.rs:834-846, 930-981): none -> no row; fewer than two or no +Inf bound last -> NaN; else
+ * evaluate_row (:1046-1118).  b2p_histogram_quantile_dev is the uniform-layout front end of the same kernel. */
+B2P_API int b2p_histogram_fold_dev(b2p_ctx* ctx, double phi, const uint32_t* hist_off, const uint32_t* bucket_series,
+                           const double* bucket_le, uint32_t n_hist, const double* rates, const uint32_t* valid_words,
+                           uint64_t T, double* out, uint32_t* out_valid_words);
 /* cols: n_cols column pointers (device array of device pointers), each n_rows f64; NaN rows are
  * skipped (SeriesNormalize filter).  out_sum[n_cols], out_cnt[n_cols] accumulate. */
 B2P_API int b2p_column_reduce_dev(b2p_ctx* ctx, const double* const* cols, uint32_t n_cols, uint64_t n_rows,
@@ -250,6 +258,12 @@ B2P_API int b2p_group_aggregate(b2p_ctx* ctx, int32_t agg, const double* vals, c
 B2P_API int b2p_histogram_quantile(b2p_ctx* ctx, double phi, const double* le, uint32_t n_buckets, const double* rates,
                            const uint32_t* valid_words, uint32_t n_hist, uint64_t T, double* out,
                            uint32_t* out_valid_words);
+/* histogram_quantile(phi, fn(bucket series)) in one call: samples in (host), rows [n_hist*T] out (host); the dense
+ * per-series matrix stays on the device between the range function and the fold.  Index arrays are host pointers. */
+B2P_API int b2p_range_histogram_fold(b2p_ctx* ctx, const b2p_range_params* p, const int64_t* ts, const double* val,
+                             const uint32_t* sid, const uint64_t* offsets_host, uint64_t n_rows, uint32_t n_series,
+                             double phi, const uint32_t* hist_off, const uint32_t* bucket_series, const double* bucket_le,
+                             uint32_t n_hist, double* out, uint32_t* out_valid_words);
 
 /* ---- plan-level API over the Arrow C Data Interface ------------------------------------------------
  * GpuPromRangeExec: the whole sub-tree SeriesDivide -> SeriesNormalize -> RangeManipulate ->

@@ -320,3 +320,81 @@ def compensated_sum(inputs):
     for x in inputs:
         lib().orc_compensated_sum_inc(float(x), C.byref(s), C.byref(c))
     return s.value, c.value
+
+
+# ---------------------------------------------------------------------------------------------------
+# HistogramFold, row-literal (small cases only): fold_buf's optimistic mode, the switch to safe mode and the safe-mode
+# grouping of histogram_fold.rs:725-981, on rows in scan order.  Used to pin the dense device fold on the reference's
+# operator tests (tests/golden/reference_histogram_fold_vectors.json).
+# ---------------------------------------------------------------------------------------------------
+def parse_f64_rust(s):
+    """str::parse::<f64>().unwrap_or(NaN) (histogram_fold.rs:791-796): decimal / exponent forms, inf / infinity / nan
+    in any case with an optional sign; no surrounding white space, hex, underscores or decimal commas."""
+    import math
+    import re
+    if s is None:
+        return math.nan
+    m = re.fullmatch(r"([+-]?)(inf|infinity|nan)", s, flags=re.I)
+    if m:
+        if m.group(2).lower() == "nan":
+            return math.nan
+        return -math.inf if m.group(1) == "-" else math.inf
+    if re.fullmatch(r"[+-]?(\d+\.?\d*|\.\d+)([eE][+-]?\d+)?", s):
+        return float(s)
+    return math.nan
+
+
+def histogram_fold_rows(rows, phi):
+    """rows: [(tags tuple, ts, le label, value)] in scan order (sorted by tags, ts, le).  -> [(tags, ts, result)].
+    A group is a run of rows with equal (tags, ts) — the reference's `normal` columns are everything but le and the field."""
+    import math
+
+    def is_pos_inf(le):
+        v = parse_f64_rust(le)
+        return math.isinf(v) and v > 0
+
+    def evaluate(buckets, counters):  # evaluate_row(..).unwrap_or(NaN)
+        v, err = histogram_evaluate_row(phi, np.array(buckets, np.float64), np.array(counters, np.float64))
+        return math.nan if err else v
+
+    n = len(rows)
+    out = []
+    # find_first_complete_bucket (:725-751): rows from the start of the group that holds the first +Inf row
+    bucket_num = None
+    group_start = 0
+    cur_key = rows[0][:2] if n else None
+    for r in range(n):
+        if rows[r][:2] != cur_key:  # new group begins
+            cur_key = rows[r][:2]
+            group_start = r
+        if is_pos_inf(rows[r][2]):
+            bucket_num = r - group_start + 1
+            break
+    cursor = 0
+    if bucket_num is not None:
+        while n - cursor >= bucket_num:  # optimistic mode (:768-812)
+            key = rows[cursor][:2]
+            ok = is_pos_inf(rows[cursor + bucket_num - 1][2]) and all(rows[cursor + o][:2] == key for o in range(1, bucket_num))
+            if not ok:
+                break
+            grp = rows[cursor:cursor + bucket_num]
+            try:
+                res = evaluate([parse_f64_rust(g[2]) for g in grp], [g[3] for g in grp])
+            except Exception:
+                res = math.nan
+            out.append((key[0], key[1], res))
+            cursor += bucket_num
+    # safe mode over what is left (:930-981): variable-length groups
+    r = cursor
+    while r < n:
+        key = rows[r][:2]
+        e = r
+        while e < n and rows[e][:2] == key:
+            e += 1
+        b = [parse_f64_rust(g[2]) for g in rows[r:e]]
+        c = [g[3] for g in rows[r:e]]
+        has_inf = len(b) > 0 and math.isinf(b[-1]) and b[-1] > 0
+        res = math.nan if (len(b) < 2 or not has_inf) else evaluate(b, c)
+        out.append((key[0], key[1], res))
+        r = e
+    return out

@@ -902,8 +902,11 @@ void orc_group_aggregate(int op, const double* vals, const uint32_t* valid_words
         case 0:
         case 1: out_val[idx] += x; break;
         case 2: break;
-        case 3: if (c == 0 || x < out_val[idx] || (isnan(out_val[idx]) && !isnan(x))) out_val[idx] = x; break;
-        case 4: if (c == 0 || x > out_val[idx] || (isnan(out_val[idx]) && !isnan(x))) out_val[idx] = x; break;
+        /* min / max: the total order of f64::total_cmp (arrow-rs aggregate min / max and DataFusion's MinMax
+         * accumulators compare floats that way): a positive NaN is the greatest value, so max() of a group with a
+         * NaN member is NaN while min() ignores it (-NaN sorts lowest).  Third-party semantics, restated. */
+        case 3: if (c == 0 || total_key(x) < total_key(out_val[idx])) out_val[idx] = x; break;
+        case 4: if (c == 0 || total_key(x) > total_key(out_val[idx])) out_val[idx] = x; break;
         default: {
           double new_count = (double)c + 1.0;
           double delta1 = x - mean[idx];

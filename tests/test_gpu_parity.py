@@ -985,3 +985,143 @@ def test_full_size_chunk_properties_and_tier_equivalence(ctx, ctx_no_lean):
     got = np.stack([r_lean[s * T:(s + 1) * T].cpu().numpy() for s in pick])
     gv = np.stack([v_lean[s * Tw:(s + 1) * Tw].cpu().numpy().view(np.uint32) for s in pick])
     assert_close(got, e_out, orc.valid_to_bool(gv, T), orc.valid_to_bool(e_valid, T), "full-size chunk sample vs oracle")
+
+
+# ---------------------------------------------------------------------------------------------------
+# HistogramFold on the device: the reference's operator tests (histogram_fold.rs:1452-1630), mixed bucket layouts,
+# the 64-bucket config-4 shape
+# ---------------------------------------------------------------------------------------------------
+def _fold_golden():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_histogram_fold_vectors.json")) as f:
+        return json.load(f)
+
+
+FOLD = _fold_golden()
+
+
+def _dense_from_rows(case):
+    """rows (group, ts, le, val) -> the dense form the device fold takes: one series per (group, le), steps = the
+    distinct (ts | explicit step) values in order, validity = a row exists."""
+    rows = case["rows"]
+    steps = case.get("step_of_row")
+    if steps is None:
+        ts_sorted = sorted({r[1] for r in rows})
+        steps = [ts_sorted.index(r[1]) for r in rows]
+    T = max(steps) + 1
+    groups = []
+    for r in rows:
+        if r[0] not in groups:
+            groups.append(r[0])
+    series = []          # (group index, le label)
+    for r in rows:
+        key = (groups.index(r[0]), r[2])
+        if key not in series:
+            series.append(key)
+    S = len(series)
+    rates = np.zeros((S, T))
+    valid = np.zeros((S, 1), np.uint32)
+    for r, k in zip(rows, steps):
+        s = series.index((groups.index(r[0]), r[2]))
+        rates[s, k] = r[3]
+        valid[s, 0] |= np.uint32(1 << k)
+    les = np.array([orc.parse_f64_rust(le) for _, le in series])
+    order = sorted(range(S), key=lambda s: (series[s][0], np.isnan(les[s]), les[s] if not np.isnan(les[s]) else 0.0))
+    hist_off = np.zeros(len(groups) + 1, np.uint32)
+    for s in order:
+        hist_off[series[s][0] + 1] += 1
+    hist_off = np.cumsum(hist_off).astype(np.uint32)
+    return groups, T, rates, valid, np.array(order, np.uint32), les[order].copy(), hist_off
+
+
+@pytest.mark.parametrize("case", FOLD["cases"], ids=lambda c: c["name"])
+def test_histogram_fold_operator_goldens_on_the_device(ctx, case):
+    import torch
+    dev = torch.device("cuda:0")
+    groups, T, rates, valid, bucket_series, bucket_le, hist_off = _dense_from_rows(case)
+    H = len(groups)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = torch.zeros(H * T, dtype=torch.float64, device=dev)
+    ov = torch.zeros(H * 1, dtype=torch.int32, device=dev)
+    ctx.use_own_stream()
+    torch.cuda.synchronize()
+    ctx.histogram_fold_dev(case["phi"], d(hist_off.astype(np.int32)), d(bucket_series.astype(np.int32)), d(bucket_le), H,
+                           d(rates), d(valid.astype(np.int32)), T, out, ov)
+    ctx.sync()
+    got, gv = out.cpu().numpy().reshape(H, T), ov.cpu().numpy().view(np.uint32).reshape(H, 1)
+    flat = [(groups[h], float(got[h, k])) for h in range(H) for k in range(T) if (gv[h, 0] >> k) & 1]
+    assert len(flat) == len(case["expected"]), (flat, case["expected"])
+    for (g, v), (eg, ev) in zip(flat, case["expected"]):
+        assert g == eg
+        if ev == "NaN":
+            assert np.isnan(v)
+        else:
+            assert abs(v - float(ev)) <= max(case["tol"], 0.0) * max(abs(float(ev)), 1.0) or v == float(ev), (case["name"], v, ev)
+
+
+def test_histogram_fold_64_buckets_and_missing_buckets_match_the_row_literal_fold(ctx):
+    """The config-4 shape (64 buckets per histogram) with holes: some bucket series have no sample at some steps, some
+    histograms lack the +Inf bucket or have fewer buckets.  The dense device fold must equal the row-literal restatement
+    of fold_buf / safe mode on the same rows."""
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(4)
+    H, T = 23, 70
+    rows, series, les, hist_of = [], [], [], []
+    for h in range(H):
+        B = [64, 64, 64, 17, 2, 1][h % 6]
+        bounds = list(np.round(0.005 * 1.3 ** np.arange(B - 1), 6)) + [np.inf]
+        if h % 7 == 3:
+            bounds[-1] = 1e9            # no +Inf bucket at all
+        for b in range(B):
+            series.append((h, b))
+            les.append(bounds[b])
+            hist_of.append(h)
+    S = len(series)
+    Tw = (T + 31) // 32
+    rates = np.zeros((S, T))
+    valid = np.zeros((S, Tw), np.uint32)
+    base = np.cumsum(rng.random((S, T)), axis=0)            # cumulative over buckets within the flat order (good enough)
+    for s, (h, b) in enumerate(series):
+        for k in range(T):
+            if rng.random() < 0.04:
+                continue                                    # hole: this bucket has no sample at this step
+            v = base[s, k] - base[[i for i, x in enumerate(series) if x[0] == h][0], k] + 1.0
+            if rng.random() < 0.01:
+                v = np.nan
+            rates[s, k] = v
+            valid[s, k >> 5] |= np.uint32(1 << (k & 31))
+    phi = 0.99
+    # row-literal fold on the same data: rows sorted by (histogram, step, le)
+    lit = []
+    for h in range(H):
+        sidx = [i for i, x in enumerate(series) if x[0] == h]
+        for k in range(T):
+            rr = [((h,), k, ("+Inf" if np.isinf(les[i]) else repr(float(les[i]))), rates[i, k]) for i in sidx
+                  if (valid[i, k >> 5] >> (k & 31)) & 1]
+            lit += rr
+    exp = {(t[0], k): v for t, k, v in orc.histogram_fold_rows(lit, phi)}
+    hist_off = np.zeros(H + 1, np.int32)
+    for h in hist_of:
+        hist_off[h + 1] += 1
+    hist_off = np.cumsum(hist_off).astype(np.int32)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = torch.zeros(H * T, dtype=torch.float64, device=dev)
+    ov = torch.zeros(H * Tw, dtype=torch.int32, device=dev)
+    ctx.use_own_stream()
+    torch.cuda.synchronize()
+    ctx.histogram_fold_dev(phi, d(hist_off), d(np.arange(S, dtype=np.int32)), d(np.array(les)), H, d(rates),
+                           d(valid.astype(np.int32)), T, out, ov)
+    ctx.sync()
+    got, gv = out.cpu().numpy().reshape(H, T), ov.cpu().numpy().view(np.uint32).reshape(H, Tw)
+    n_rows = 0
+    for h in range(H):
+        for k in range(T):
+            has = bool((gv[h, k >> 5] >> (k & 31)) & 1)
+            assert has == ((h, k) in exp), (h, k)
+            if has:
+                n_rows += 1
+                e, g = exp[(h, k)], got[h, k]
+                assert (np.isnan(e) and np.isnan(g)) or e == g or abs(e - g) <= 1e-12 * abs(e), (h, k, e, g)
+    assert n_rows > H * T // 2

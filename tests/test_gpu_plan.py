@@ -152,3 +152,96 @@ def test_instant_selector_through_the_plan(ctx):
     rows = list(zip(out.column(2).to_pylist(), [int(t.timestamp() * 1000) for t in out.column(0).to_pylist()],
                     out.column(1).to_pylist()))
     assert rows == [tuple(r) for r in case["expected"]]
+
+
+# ---------------------------------------------------------------------------------------------------
+# by-label aggregators: the reference's result tables (tests-integration/src/tests/promql_test.rs:343-665) through the
+# plan layer — instant selector (lookback 0) + Aggregate + Sort on the GPU
+# ---------------------------------------------------------------------------------------------------
+def _aggr_golden():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_aggregator_vectors.json")) as f:
+        return json.load(f)
+
+
+AGGR = _aggr_golden()
+
+
+@pytest.mark.parametrize("case", AGGR["cases"], ids=lambda c: c["name"])
+def test_by_label_aggregators_reference_tables_through_the_plan(ctx, case):
+    from greptimedb_b200.plan import PromRangeExec
+    sel = [s for s in AGGR["series"] if all(s[k] == v for k, v in case["filter"].items())]   # the label matcher
+    sel.sort(key=lambda s: tuple(s[t] for t in AGGR["tags"]))                                   # scan order
+    cols = {t: [] for t in AGGR["tags"]}
+    ts, val = [], []
+    for s in sel:
+        ts += s["ts"]
+        val += s["val"]
+        for t in AGGR["tags"]:
+            cols[t] += [s[t]] * len(s["ts"])
+    b = pa.record_batch([pa.array(ts, pa.timestamp("ms")), pa.array(val, pa.float64())] + [pa.array(cols[t]) for t in AGGR["tags"]],
+                        names=[AGGR["time_index"], AGGR["field"]] + AGGR["tags"])
+    ex = PromRangeExec(ctx, "", AGGR["start"], AGGR["end"], AGGR["interval"], 0, AGGR["time_index"], AGGR["field"],
+                       AGGR["tags"], lookback_delta=AGGR["lookback"], aggregate=case["agg"], by_columns=case["by"])
+    ex.push(b)
+    out = ex.execute()
+    nby = len(case["by"])
+    assert out.schema.names[:nby] == case["by"]
+    keys = list(zip(*[out.column(i).to_pylist() for i in range(nby)])) if nby else [()] * out.num_rows
+    tss = [int(t.timestamp() * 1000) for t in out.column(nby).to_pylist()]
+    got = {(tuple(k), t): v for k, t, v in zip(keys, tss, out.column(nby + 1).to_pylist())}
+    assert list(zip(keys, tss)) == sorted(zip(keys, tss))        # .sort(group_exprs asc) — planner.rs:443-449
+    exp = {(tuple(lbl[bcol] for bcol in case["by"]), int(t)): float(v) for lbl, t, v in case["expected"]}
+    assert set(got) == set(exp), (sorted(got), sorted(exp))
+    tol = case.get("rel_tol", 0.0)
+    for k in exp:
+        assert abs(got[k] - exp[k]) <= tol * abs(exp[k]), (k, got[k], exp[k])
+
+
+def test_histogram_fold_plan_mixed_layouts_and_strict_le_parse(ctx):
+    """Histograms with different bucket layouts in one query (the reference's safe mode, histogram_fold.rs:834-846) and le
+    labels only Rust's f64 parse accepts: ' 2' (leading blank) and '0x4' are NaN bounds -> the row is NaN; '+inf', '1e0'
+    parse.  Buckets arrive in the scan's string order and are folded in numeric le order."""
+    from greptimedb_b200.plan import PromRangeExec
+    T0, N = 1_700_000_000_000, 40
+    tsv = [T0 + i * 15_000 for i in range(N)]
+    hists = {"a": ["0.5", "1e0", "2", "+inf"], "b": ["1", "+Inf"], "c": ["0.5", " 2", "+Inf"], "d": ["0.5", "1"]}
+    ts, val, host, le = [], [], [], []
+    for hname, les in sorted(hists.items()):
+        for j, l in enumerate(sorted(les)):                      # primary-key (string) order within the histogram
+            rank = sorted(les, key=lambda x: (np.isnan(orc.parse_f64_rust(x)), orc.parse_f64_rust(x))).index(l)
+            for i in range(N):
+                ts.append(tsv[i])
+                val.append(float((rank + 1) * (i + 1) * (1 + ord(hname) % 3)))
+                host.append(hname)
+                le.append(l)
+    b = pa.record_batch([pa.array(ts, pa.timestamp("ms")), pa.array(val, pa.float64()), pa.array(host), pa.array(le)],
+                        names=["ts", "val", "host", "le"])
+    start, end, step, rng = T0 + 300_000, T0 + (N - 1) * 15_000, 60_000, 300_000
+    ex = PromRangeExec(ctx, "prom_rate", start, end, step, rng, "ts", "val", ["host", "le"], histogram_quantile=0.5)
+    ex.push(b)
+    out = ex.execute()
+    assert out.schema.names == ["ts", "prom_rate(ts_range,val)", "host"]
+    got = {}
+    for t, v, hname in zip(out.column(0).to_pylist(), out.column(1).to_pylist(), out.column(2).to_pylist()):
+        got[(hname, int(t.timestamp() * 1000))] = v
+    # expectation: rate per bucket series from the oracle, then the row-literal fold
+    rows = []
+    for hname, les in sorted(hists.items()):
+        for l in les:
+            sel = [i for i in range(len(ts)) if host[i] == hname and le[i] == l]
+            st, sv = np.array([ts[i] for i in sel], np.int64), np.array([val[i] for i in sel])
+            op = orc.make_params("rate", start, end, step, rng)
+            o, v = orc.range_query(op, st, sv, None, np.array([0, st.size], np.uint64))
+            for k in range(o.shape[1]):
+                if (v[0, k >> 5] >> (k & 31)) & 1:
+                    rows.append(((hname,), start + k * step, l, o[0, k]))
+    rows.sort(key=lambda r: (r[0], r[1], np.isnan(orc.parse_f64_rust(r[2])), orc.parse_f64_rust(r[2]) if not np.isnan(orc.parse_f64_rust(r[2])) else 0.0))
+    exp = {(t[0], tsx): v for t, tsx, v in orc.histogram_fold_rows(rows, 0.5)}
+    assert set(got) == set(exp)
+    for k in exp:
+        e, g = exp[k], got[k]
+        assert (np.isnan(e) and np.isnan(g)) or abs(e - g) <= 1e-9 * abs(e), (k, e, g)
+    assert all(np.isnan(v) for (hname, _), v in got.items() if hname in ("c", "d"))      # NaN bound / no +Inf bucket
+    assert not any(np.isnan(v) for (hname, _), v in got.items() if hname in ("a", "b"))

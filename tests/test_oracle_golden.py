@@ -231,3 +231,126 @@ def test_synth_generator_matches_reference_bench_recurrence():
             ref.append(cur * (1 + s % 13))
         assert val.tolist() == ref
         assert (ts == np.arange(n) * 15000).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# by-label aggregators: the reference's own result tables (tests-integration/src/tests/promql_test.rs:343-665)
+# ---------------------------------------------------------------------------------------------------
+def _load_aggr():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_aggregator_vectors.json")) as f:
+        return json.load(f)
+
+
+AGGR = _load_aggr()
+
+
+def aggregator_case_inputs(case):
+    """series passing the label matcher, sorted by tag tuple like the scan; dense group ids of the by-labels."""
+    sel = [s for s in AGGR["series"] if all(s[k] == v for k, v in case["filter"].items())]
+    sel.sort(key=lambda s: tuple(s[t] for t in AGGR["tags"]))
+    keys = sorted({tuple(s[b] for b in case["by"]) for s in sel})
+    gid = np.array([keys.index(tuple(s[b] for b in case["by"])) for s in sel], np.uint32)
+    ts = np.concatenate([np.array(s["ts"], np.int64) for s in sel])
+    val = np.concatenate([np.array(s["val"], np.float64) for s in sel])
+    offsets = np.concatenate([[0], np.cumsum([len(s["ts"]) for s in sel])]).astype(np.uint64)
+    return sel, keys, gid, ts, val, offsets
+
+
+def check_aggregator_rows(case, keys, out, cnt, ets):
+    got = {}
+    for g, key in enumerate(keys):
+        for k in range(out.shape[1]):
+            if cnt[g, k] > 0:
+                got[(key, int(ets[k]))] = float(out[g, k])
+    exp = {(tuple(lbl[b] for b in case["by"]), int(t)): float(v) for lbl, t, v in case["expected"]}
+    assert set(got) == set(exp), (case["name"], sorted(got), sorted(exp))
+    tol = case.get("rel_tol", 0.0)
+    for k in exp:
+        assert abs(got[k] - exp[k]) <= tol * abs(exp[k]), (case["name"], k, got[k], exp[k])
+
+
+@pytest.mark.parametrize("case", AGGR["cases"], ids=lambda c: c["name"])
+def test_by_label_aggregators_reference_tables(case):
+    """InstantManipulate (lookback 0) + the by-label aggregate of the oracle == the reference's result tables: pins
+    orc_group_aggregate (the restatement of DataFusion's sum / avg / count / min / max / stddev_pop / var_pop
+    accumulators) on groups with several members."""
+    sel, keys, gid, ts, val, offsets = aggregator_case_inputs(case)
+    out, valid = orc.instant_query(ts, val, offsets, AGGR["start"], AGGR["end"], AGGR["interval"], AGGR["lookback"])
+    ets = AGGR["start"] + AGGR["interval"] * np.arange(out.shape[1])
+    agg, cnt = orc.group_aggregate(case["agg"], out, valid, gid, len(keys))
+    check_aggregator_rows(case, keys, agg, cnt, ets)
+
+
+def test_by_label_aggregators_combined_expressions():
+    by_name = {c["name"]: c for c in AGGR["cases"]}
+    vals = {}
+    for name in ("combined_sum_by_job", "combined_min_by_job", "combined_max_by_job", "combined_avg_by_job"):
+        case = by_name[name]
+        sel, keys, gid, ts, val, offsets = aggregator_case_inputs(case)
+        out, valid = orc.instant_query(ts, val, offsets, AGGR["start"], AGGR["end"], AGGR["interval"], AGGR["lookback"])
+        agg, cnt = orc.group_aggregate(case["agg"], out, valid, gid, len(keys))
+        vals[case["agg"]] = {k[0]: float(agg[g, 0]) for g, k in enumerate(keys)}
+    four, two = AGGR["combined_checks"]
+    for job, exp in four["expected"].items():
+        assert vals["sum"][job] + vals["min"][job] + vals["max"][job] + vals["avg"][job] == exp
+    for job, exp in two["expected"].items():
+        assert vals["sum"][job] + vals["min"][job] == exp
+
+
+def test_min_max_by_label_follow_the_total_order_on_nan_members():
+    """arrow-rs aggregate min / max and DataFusion's MinMax accumulators compare floats with f64::total_cmp: a (positive)
+    NaN is the greatest value.  max by (..) of a group with a NaN member is NaN, min by (..) ignores it."""
+    vals = np.array([[1.0], [np.nan], [3.0], [2.0]])
+    valid = np.ones((4, 1), np.uint32)
+    gid = np.zeros(4, np.uint32)
+    mx, c = orc.group_aggregate("max", vals, valid, gid, 1)
+    mn, _ = orc.group_aggregate("min", vals, valid, gid, 1)
+    assert c[0, 0] == 4 and np.isnan(mx[0, 0]) and mn[0, 0] == 1.0
+    neg_nan = np.frombuffer(np.uint64(0xfff8000000000000).tobytes(), np.float64)[0]
+    vals[1, 0] = neg_nan                       # -NaN sorts below everything
+    mx, _ = orc.group_aggregate("max", vals, valid, gid, 1)
+    mn, _ = orc.group_aggregate("min", vals, valid, gid, 1)
+    assert mx[0, 0] == 3.0 and np.isnan(mn[0, 0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# HistogramFold operator tests (histogram_fold.rs:1452-1630) and the le-label parse
+# ---------------------------------------------------------------------------------------------------
+def _load_fold():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_histogram_fold_vectors.json")) as f:
+        return json.load(f)
+
+
+FOLD = _load_fold()
+
+
+def _fnum(x):
+    return float("nan") if x == "NaN" else float(x)
+
+
+@pytest.mark.parametrize("case", FOLD["cases"], ids=lambda c: c["name"])
+def test_histogram_fold_operator_goldens(case):
+    rows = [((r[0],), r[1], r[2], r[3]) for r in case["rows"]]
+    got = orc.histogram_fold_rows(rows, case["phi"])
+    assert len(got) == len(case["expected"])
+    for (tags, ts, v), (etag, ev) in zip(got, case["expected"]):
+        assert tags == (etag,)
+        ev = _fnum(ev)
+        if np.isnan(ev):
+            assert np.isnan(v)
+        else:
+            assert abs(v - ev) <= case["tol"] * max(abs(ev), 1.0) + (0.0 if case["tol"] else 0.0), (case["name"], v, ev)
+
+
+def test_le_label_parse_follows_rust():
+    lp = FOLD["le_parse"]
+    for s, v in lp["finite"].items():
+        assert orc.parse_f64_rust(s) == v, s
+    for s in lp["inf"]:
+        assert orc.parse_f64_rust(s) == float("inf"), s
+    for s in lp["nan"]:
+        assert np.isnan(orc.parse_f64_rust(s)), repr(s)
