@@ -234,6 +234,54 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
+def gpu_numa_cpus(local: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None.  Pinned staging buffers first-touched from these CPUs
+    land in host memory next to the GPU's PCIe root: with eight ranks copying at once, remote-node traffic was what
+    held 8-GPU end-to-end efficiency at 0.59 in round 1."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        return (node, cpus) if cpus else None
+    except Exception:
+        return None
+
+
+class numa_local:
+    """with numa_local(local): allocate + first-touch host buffers on the GPU's NUMA node, then restore the affinity."""
+
+    def __init__(self, local):
+        self.info = gpu_numa_cpus(local)
+        self.saved = None
+
+    def __enter__(self):
+        if self.info:
+            try:
+                self.saved = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.info[1] & self.saved or self.info[1])
+            except Exception:
+                self.saved = None
+        return self.info[0] if self.info else None
+
+    def __exit__(self, *exc):
+        if self.saved:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:
+                pass
+        return False
+
+
 class Harness:
     """Per-process state shared by the config benches: device, context, distributed plumbing, timing helper."""
 
@@ -344,20 +392,25 @@ def bench_config2(h: Harness, sampler):
     res["e2e"] = None
     if Se > 0:
         import ctypes as C
-        h_ts = torch.empty(Se * N_SAMPLES, dtype=torch.int64).pin_memory()
-        h_val = torch.empty(Se * N_SAMPLES, dtype=torch.float64).pin_memory()
-        h_sid = torch.empty(Se * N_SAMPLES, dtype=torch.int32).pin_memory()
-        h_out = torch.empty(Se * T, dtype=torch.float64).pin_memory()
-        h_valid = torch.empty(Se * Tw, dtype=torch.int32).pin_memory()
-        h_ts.copy_(ts[: Se * N_SAMPLES])
-        h_val.copy_(val[: Se * N_SAMPLES])
-        h_sid.copy_(sid[: Se * N_SAMPLES])
+        with numa_local(h.local) as numa_node:   # pinned staging next to this GPU's PCIe root
+            h_ts = torch.empty(Se * N_SAMPLES, dtype=torch.int64).pin_memory()
+            h_val = torch.empty(Se * N_SAMPLES, dtype=torch.float64).pin_memory()
+            h_sid = torch.empty(Se * N_SAMPLES, dtype=torch.int32).pin_memory()
+            h_out = torch.empty(Se * T, dtype=torch.float64).pin_memory()
+            h_valid = torch.empty(Se * Tw, dtype=torch.int32).pin_memory()
+            h_out.zero_()
+            h_valid.zero_()
+            h_ts.copy_(ts[: Se * N_SAMPLES])
+            h_val.copy_(val[: Se * N_SAMPLES])
+            h_sid.copy_(sid[: Se * N_SAMPLES])
+            h_off = (torch.arange(Se + 1, dtype=torch.int64) * N_SAMPLES).pin_memory()
         torch.cuda.synchronize()
         L = ctx._L
 
-        def e2e_step():
+        def e2e_step(with_offsets=False):
             rc = L.b2p_range_eval(ctx._h, C.byref(p), C.c_void_p(h_ts.data_ptr()), C.c_void_p(h_val.data_ptr()),
-                                  C.c_void_p(h_sid.data_ptr()), None, Se * N_SAMPLES, Se,
+                                  None if with_offsets else C.c_void_p(h_sid.data_ptr()),
+                                  C.c_void_p(h_off.data_ptr()) if with_offsets else None, Se * N_SAMPLES, Se,
                                   C.c_void_p(h_out.data_ptr()), C.c_void_p(h_valid.data_ptr()), None)
             if rc != 0:
                 raise RuntimeError(L.b2p_last_error().decode())
@@ -371,10 +424,20 @@ def bench_config2(h: Harness, sampler):
             e2e_step()          # synchronous: returns after the D2H of the result
         torch.cuda.synchronize()
         dt = h.max_over_ranks(time.perf_counter() - t0)
+        # the same call when the caller (SeriesDivide's boundaries are known to it) hands over series offsets instead of
+        # the 4 B/row id column: 16 B/sample over PCIe and no K0
+        h.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step(True)
+        torch.cuda.synchronize()
+        dt_off = h.max_over_ranks(time.perf_counter() - t0)
         res["e2e"] = {"value": Se * N_SAMPLES * h.world * n_e2e / dt, "unit": UNIT,
                       "h2d_bytes_per_step": Se * N_SAMPLES * 20, "d2h_bytes_per_step": Se * T * 8 + Se * Tw * 4,
-                      "series_per_step": Se, "steps": n_e2e}
-        del h_ts, h_val, h_sid, h_out, h_valid
+                      "series_per_step": Se, "steps": n_e2e, "pinned_numa_node": numa_node,
+                      "with_series_offsets_instead_of_ids": {"value": Se * N_SAMPLES * h.world * n_e2e / dt_off,
+                                                             "h2d_bytes_per_step": Se * N_SAMPLES * 16 + (Se + 1) * 8}}
+        del h_ts, h_val, h_sid, h_out, h_valid, h_off
     del ts, val, sid, offsets, out, valid
     h.free()
     return res

@@ -270,7 +270,47 @@ __global__ void __launch_bounds__(kHistWarps * 32) histogram_fold_kernel(const H
     bool sorted = true;      // bucket.windows(2).all(|w| w[0] <= w[1]) over the present bounds
     bool ok = false;
     double r = 0.0;
-    if (nb <= (uint32_t)kHistSmemBuckets) {
+    // common case first: all buckets of the histogram have samples at the same steps of the tile (normally: at every
+    // step) -> a step either has no row or every bucket: no per-lane compaction, slot = bucket
+    uint32_t all = 0xffffffffu, any = 0u;
+    for (uint32_t b0 = 0; b0 < nb; b0 += 32) {
+      const bool has = b0 + lane < nb;
+      const uint32_t wv = has ? a.valid[(size_t)bs[b0 + lane] * a.Tw + tile] : 0u;
+      all &= __reduce_and_sync(0xffffffffu, has ? wv : 0xffffffffu);
+      any |= __reduce_or_sync(0xffffffffu, wv);
+    }
+    if (nb <= (uint32_t)kHistSmemBuckets && all == any && nb >= 2) {
+      const bool present = in && ((all >> lane) & 1u);
+      for (uint32_t b0 = 0; b0 < nb; b0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          v[u] = (b0 + u < nb && present) ? __ldcs(a.rates + (size_t)bs[b0 + u] * a.T + k) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (b0 + u < nb) {
+            double c = isfinite(v[u]) ? v[u] : prev;
+            if (b0 + u > 0 && c < prev) c = prev;
+            prev = c;
+            col[(b0 + u) * 32] = c;
+          }
+        }
+      }
+      // the bounds of the histogram are the same for every lane: sortedness and the +Inf check once per warp
+      bool srt = true;
+      for (uint32_t b0 = 0; b0 + 1 < nb; b0 += 32) {
+        const bool okp = (b0 + lane + 1 < nb) ? (ble[b0 + lane] <= ble[b0 + lane + 1]) : true;
+        srt = srt && __all_sync(0xffffffffu, okp);
+      }
+      const double l_last = ble[nb - 1];
+      const bool has_inf = l_last == __longlong_as_double(0x7ff0000000000000ll);
+      ok = present;
+      if (ok) {
+        if (!has_inf) r = kNaN;
+        else if (!srt && !(a.phi < 0.0) && !(a.phi > 1.0)) r = kNaN;
+        else r = histogram_row(a.phi, nb, [&](uint32_t i) { return col[i * 32]; }, [&](uint32_t i) { return ble[i]; });
+      }
+    } else if (nb <= (uint32_t)kHistSmemBuckets) {
       for (uint32_t b0 = 0; b0 < nb; b0 += 8) {
         double v[8];
         uint32_t wd[8];

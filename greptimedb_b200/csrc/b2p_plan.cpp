@@ -252,49 +252,67 @@ void PromRangePlan::push(std::unique_ptr<RecordBatch> batch) {
     return std::string(tc.data + tc.off[r], (size_t)(tc.off[r + 1] - tc.off[r]));
   };
 
-  ts_.reserve(ts_.size() + (size_t)n);
-  val_.reserve(val_.size() + (size_t)n);
-  sid_.reserve(sid_.size() + (size_t)n);
-  for (int64_t row = 0; row < n; ++row) {
-    // SeriesDivide: a new series starts wherever the key differs from the previous row's
-    // (find_first_diff_row compares adjacent rows, series_divide.rs:658-667, and the first row of a
-    // batch with the last row of the previous one, :636-645)
-    bool new_series = !have_last_;
-    if (key_is_id_) {
-      const uint64_t id = tcols[0].ids[tcols[0].base + row];
-      if (have_last_ && id != last_id_) new_series = true;
-      if (new_series) tags_.tsid.push_back(id);
-      last_id_ = id;
-    } else if (!tcols.empty()) {
-      if (have_last_) {
-        for (size_t t = 0; t < tcols.size() && !new_series; ++t) {
-          const TagCol& tc = tcols[t];
-          const int64_t r = tc.base + row;
-          const bool v = bit_set(tc.valid, r);
-          const std::string& last = last_key_[t];
-          if (!v) {
-            if (last != std::string("\0null", 5)) new_series = true;
-          } else {
-            const size_t len = (size_t)(tc.off[r + 1] - tc.off[r]);
-            if (last.size() != len || std::memcmp(last.data(), tc.data + tc.off[r], len) != 0) new_series = true;
-          }
-        }
-      }
-      if (new_series) {
-        last_key_.resize(tcols.size());
-        for (size_t t = 0; t < tcols.size(); ++t) {
-          last_key_[t] = tag_at(t, row);
-          tags_.utf8[t].push_back(last_key_[t]);
-        }
-      }
-    }
-    if (new_series) ++num_series_;  // no tag columns: the whole input is one series (series_divide.rs:624-627)
-    have_last_ = true;
-    ts_.push_back(tsv[row]);
-    // a NULL field value cannot be inside a window: treat it like the NaN the filter drops
-    val_.push_back(bit_set(fvalid, fa.offset + b.offset() + row) ? fv[row] : std::nan(""));
-    sid_.push_back((uint32_t)(num_series_ - 1));
+  // Columns are taken over in bulk (the Arrow values buffers are already the device layout): one memcpy per column
+  // and batch, no per-row growth.  SeriesDivide only has to find the rows where a new series starts
+  // (find_first_diff_row compares adjacent rows, series_divide.rs:658-667, and the first row of a batch with the last
+  // row of the previous one, :636-645); the result is the offsets array the device kernels take — the 4 B/row id
+  // column is never built nor shipped.
+  const size_t row_base = ts_.size();
+  ts_.insert(ts_.end(), tsv, tsv + n);
+  val_.insert(val_.end(), fv, fv + n);
+  if (fvalid) {  // a NULL field value cannot be inside a window: treat it like the NaN the filter drops
+    for (int64_t row = 0; row < n; ++row)
+      if (!bit_set(fvalid, fa.offset + b.offset() + row)) val_[row_base + (size_t)row] = std::nan("");
   }
+  auto start_series = [&](int64_t row) {
+    offsets_.push_back((uint64_t)(row_base + (size_t)row));
+    ++num_series_;
+  };
+  if (key_is_id_) {
+    const uint64_t* ids = tcols[0].ids + tcols[0].base;
+    int64_t row = 0;
+    if (!have_last_ || ids[0] != last_id_) {
+      tags_.tsid.push_back(ids[0]);
+      start_series(0);
+    }
+    for (row = 1; row < n; ++row)
+      if (ids[row] != ids[row - 1]) {  // (a tight compare loop the compiler vectorises)
+        tags_.tsid.push_back(ids[row]);
+        start_series(row);
+      }
+    last_id_ = ids[n - 1];
+  } else if (!tcols.empty()) {
+    // adjacent-row compare on the raw Utf8 buffers; label strings are only materialised for the first row of a series
+    auto same_as_prev = [&](int64_t row) -> bool {  // row >= 1
+      for (const TagCol& tc : tcols) {
+        const int64_t r = tc.base + row;
+        const bool v = bit_set(tc.valid, r), pv = bit_set(tc.valid, r - 1);
+        if (v != pv) return false;
+        if (!v) continue;
+        const int32_t len = tc.off[r + 1] - tc.off[r];
+        if (len != tc.off[r] - tc.off[r - 1]) return false;
+        if (std::memcmp(tc.data + tc.off[r], tc.data + tc.off[r - 1], (size_t)len) != 0) return false;
+      }
+      return true;
+    };
+    auto same_as_last_key = [&]() -> bool {  // first row of this batch against the previous batch's last row
+      for (size_t t = 0; t < tcols.size(); ++t)
+        if (tag_at(t, 0) != last_key_[t]) return false;
+      return true;
+    };
+    auto open_series = [&](int64_t row) {
+      for (size_t t = 0; t < tcols.size(); ++t) tags_.utf8[t].push_back(tag_at(t, row));
+      start_series(row);
+    };
+    if (!have_last_ || !same_as_last_key()) open_series(0);
+    for (int64_t row = 1; row < n; ++row)
+      if (!same_as_prev(row)) open_series(row);
+    last_key_.resize(tcols.size());
+    for (size_t t = 0; t < tcols.size(); ++t) last_key_[t] = tag_at(t, n - 1);
+  } else if (!have_last_) {
+    start_series(0);  // no tag columns: the whole input is one series (series_divide.rs:624-627)
+  }
+  have_last_ = true;
 }
 
 void PromRangePlan::execute(ArrowArray* out, ArrowSchema* out_schema) {
@@ -311,6 +329,8 @@ void PromRangePlan::execute(ArrowArray* out, ArrowSchema* out_schema) {
   p.param1 = args_.param1;
   const int64_t T = b2p_num_steps(p.start, p.end, p.interval);
   const uint32_t S = (uint32_t)num_series_;
+  offsets_.resize((size_t)S);          // (a previous execute() appended the end marker)
+  offsets_.push_back((uint64_t)ts_.size());
   const uint32_t Tw = (uint32_t)((T + 31) / 32);
   const bool fold_on_device = args_.histogram && fn_id_ >= 0;  // the dense matrix then never reaches the host
   std::vector<double> dense(fold_on_device ? 0 : (size_t)S * (size_t)T);
@@ -319,11 +339,11 @@ void PromRangePlan::execute(ArrowArray* out, ArrowSchema* out_schema) {
   if (S > 0 && T > 0 && !(args_.histogram && fn_id_ >= 0)) {
     int rc;
     if (fn_id_ >= 0) {
-      rc = b2p_range_eval(ctx_, &p, ts_.data(), val_.data(), sid_.data(), nullptr, ts_.size(), S, dense.data(),
+      rc = b2p_range_eval(ctx_, &p, ts_.data(), val_.data(), nullptr, offsets_.data(), ts_.size(), S, dense.data(),
                           valid.data(), eval_ts.data());
     } else {  // InstantManipulate
       rc = b2p_instant_select(ctx_, p.start, p.end, p.interval, args_.lookback_delta, p.offset, ts_.data(),
-                              val_.data(), sid_.data(), nullptr, ts_.size(), S, dense.data(), valid.data());
+                              val_.data(), nullptr, offsets_.data(), ts_.size(), S, dense.data(), valid.data());
       for (int64_t k = 0; k < T; ++k) eval_ts[(size_t)k] = p.start + k * p.interval;
     }
     if (rc == B2P_E_INVALID || rc == B2P_E_TOO_LARGE) throw PlanError(ErrorKind::Plan, b2p_last_error());
@@ -400,7 +420,7 @@ void PromRangePlan::execute(ArrowArray* out, ArrowSchema* out_schema) {
     std::vector<uint32_t> hqv((size_t)H * Tw);
     if (H > 0 && T > 0) {
       if (fn_id_ < 0) throw PlanError(ErrorKind::Plan, "HistogramFold over an instant selector is not supported by this node");
-      const int rc = b2p_range_histogram_fold(ctx_, &p, ts_.data(), val_.data(), sid_.data(), nullptr, ts_.size(), S,
+      const int rc = b2p_range_histogram_fold(ctx_, &p, ts_.data(), val_.data(), nullptr, offsets_.data(), ts_.size(), S,
                                               args_.quantile, hist_off.data(), bucket_series.data(), bucket_le.data(), H,
                                               hq.data(), hqv.data());
       if (rc == B2P_E_INVALID || rc == B2P_E_TOO_LARGE) throw PlanError(ErrorKind::Plan, b2p_last_error());

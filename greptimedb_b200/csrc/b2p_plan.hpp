@@ -106,7 +106,7 @@ class PromRangePlan {
   int agg_id_;
   std::vector<int64_t> ts_;
   std::vector<double> val_;
-  std::vector<uint32_t> sid_;
+  std::vector<uint64_t> offsets_;  // first row of every series (SeriesDivide's output), end marker added by execute()
   TagStore tags_;
   bool key_is_id_ = false;
   int64_t num_series_ = 0;
