@@ -62,3 +62,16 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle/" not in txt.replace("oracle/promql_oracle.c:orc_synth_fill", "") or f.endswith(".cuh"), f
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_rust_shim_layout_assertions_compile():
+    """rust-shim/tests/layout.c static-asserts every layout rust-shim/src/ffi.rs assumes about the header."""
+    import subprocess
+    subprocess.check_call(["gcc", "-std=c11", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "rust-shim", "tests", "layout.c")])
+
+
+def test_rust_ffi_declares_every_header_symbol():
+    src = open(os.path.join(ROOT, "rust-shim", "src", "ffi.rs")).read()
+    declared = set(re.findall(r"pub fn (b2p_[a-z0-9_]+)\s*\(", src))
+    assert sorted(declared) == _declared_symbols()
