@@ -330,14 +330,14 @@ int launch_lean(b2p_ctx* c, const RangeArgs& a) {
   if (cached == 0) {
     int nb = 0;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarpsPerCta * 32, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kLeanWarps * 32, smem));
     cached = nb > 0 ? nb : 1;
   }
-  const unsigned need = (a.n_series + kWarpsPerCta - 1) / kWarpsPerCta;
+  const unsigned need = (a.n_series + kLeanWarps - 1) / kLeanWarps;
   const unsigned cap = (unsigned)(c->num_sms * cached);
   const unsigned grid = need < cap ? need : cap;
   if (grid == 0) return B2P_OK;
-  kern<<<grid, kWarpsPerCta * 32, smem, c->stream>>>(a);
+  kern<<<grid, kLeanWarps * 32, smem, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
   return B2P_OK;
@@ -369,15 +369,15 @@ int launch_lean_grouped(b2p_ctx* c, const RangeArgs& a) {
   if (cached == 0) {
     int nb = 0;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarpsPerCta * 32, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kLeanWarps * 32, smem));
     cached = nb > 0 ? nb : 1;
   }
   const unsigned n_g = a.g_hi - a.g_lo;
-  const unsigned need = (n_g + kWarpsPerCta - 1) / kWarpsPerCta;
+  const unsigned need = (n_g + kLeanWarps - 1) / kLeanWarps;
   const unsigned cap = (unsigned)(c->num_sms * cached);
   const unsigned grid = need < cap ? need : cap;
   if (grid == 0) return B2P_OK;
-  kern<<<grid, kWarpsPerCta * 32, smem, c->stream>>>(a);
+  kern<<<grid, kLeanWarps * 32, smem, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
   return B2P_OK;
@@ -796,7 +796,7 @@ static bool fused_group_ok(b2p_ctx* c, const b2p_range_params* p, int64_t T, con
   if (!lean_ok(c, p->fn_id, a)) return false;
   if (c->lean_backoff[p->fn_id] > 0 && c->lean_mode[p->fn_id] == 2) return false;
   // a group is walked by ONE warp: the largest group may not exceed a few times a warp's fair share
-  const uint64_t warps = (uint64_t)c->num_sms * 3 * kWarpsPerCta;
+  const uint64_t warps = (uint64_t)c->num_sms * B2P_LEAN_MIN_BLOCKS * kLeanWarps;
   const uint64_t share = idx->n_series / warps + 1;
   return (uint64_t)idx->max_members <= 8 * share + 64;
 }

@@ -33,10 +33,23 @@
 
 namespace b2p {
 
+// Warps per CTA of the first tier and resident CTAs per SM, tuned together with the register budget: ONE CTA of 24
+// warps per SM (80 registers).  Measured on the BASELINE shape (profiles/r2_range_lean_kernel.md): 3 x 8 warps 8.51 ms,
+// 2 x 12 warps 8.28 ms, 1 x 24 warps 7.88 ms, 1 x 28 warps (72 registers) 7.91 ms, 1 x 32 warps (64 registers) 8.04 ms —
+// the warps of a CTA work on ADJACENT series, so with one CTA the SM's concurrent streams (ts, val, out) each stay
+// inside one contiguous 192 KB region instead of three regions megabytes apart.  (B2P_LEAN_CONTIG = 1 additionally
+// gives every CTA one contiguous range of series over time: no measurable difference, off.)
 #ifndef B2P_LEAN_MIN_BLOCKS
-#define B2P_LEAN_MIN_BLOCKS 3
+#define B2P_LEAN_MIN_BLOCKS 1
 #endif
 constexpr int kLeanRing = 256;
+#ifndef B2P_LEAN_CONTIG
+#define B2P_LEAN_CONTIG 0
+#endif
+#ifndef B2P_LEAN_WARPS
+#define B2P_LEAN_WARPS 24
+#endif
+constexpr int kLeanWarps = B2P_LEAN_WARPS;
 // dynamic shared memory of one CTA: value ring + mirrored timestamp ring + reciprocal table + staging (two 64-row
 // blocks per warp and column) + bit words
 // GROUPED (fused by-label partials): per-warp counters "members of the current group whose 32-step word k/32 was valid
@@ -45,8 +58,8 @@ constexpr int kLeanRing = 256;
 constexpr int kLeanFullWords = 256;  // => T <= 8192 eval steps on the fused path (host gate)
 __host__ __device__ constexpr size_t lean_grouped_smem_bytes();
 __host__ __device__ constexpr size_t lean_smem_bytes() {
-  return (size_t)kWarpsPerCta * kLeanRing * 16 + kRcpTable * 8 + (size_t)kWarpsPerCta * 2 * 64 * 16 +
-         (size_t)kWarpsPerCta * (kLeanRing / 32) * 4;
+  return (size_t)kLeanWarps * kLeanRing * 16 + kRcpTable * 8 + (size_t)kLeanWarps * 2 * 64 * 16 +
+         (size_t)kLeanWarps * (kLeanRing / 32) * 4;
 }
 
 // The per-warp sample ring of this tier.  Timestamps (uint32 ms since start - range) are stored twice, slot p
@@ -403,7 +416,7 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
 }
 
 template <int FN, bool FLAGS, bool GROUPED = false>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_lean_kernel(const RangeArgs a) {
+__global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_lean_kernel(const RangeArgs a) {
   using LeanRing = LeanRingT<FLAGS>;
   constexpr int RING = kLeanRing;
   using TR = FnTraits<FN>;
@@ -413,11 +426,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
   //       [warps][2][64] val f64 (staging of the block being fetched and the block being consumed) |
   //       [warps][RING/32] reset / change bit words (FLAGS variant)
   double* rval = reinterpret_cast<double*>(smem_raw) + warp * RING;
-  uint32_t* rts = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kWarpsPerCta * RING * 8) + warp * (2 * RING);
-  double* rcp_tab = reinterpret_cast<double*>(smem_raw + (size_t)kWarpsPerCta * RING * 16);
+  uint32_t* rts = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kLeanWarps * RING * 8) + warp * (2 * RING);
+  double* rcp_tab = reinterpret_cast<double*>(smem_raw + (size_t)kLeanWarps * RING * 16);
   // staging slots of this lane (shared-space byte addresses): [2 halves][64] per warp and column, 8 B elements
   const uint32_t stage_t = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable) + (uint32_t)(warp * 128 + lane) * 8u;
-  const uint32_t stage_v = stage_t + (uint32_t)kWarpsPerCta * 128u * 8u;
+  const uint32_t stage_v = stage_t + (uint32_t)kLeanWarps * 128u * 8u;
   for (int i = threadIdx.x; i < kRcpTable; i += blockDim.x) rcp_tab[i] = (i > 0) ? 1.0 / (double)i : 0.0;
   __syncthreads();
   LeanRing acc;
@@ -425,7 +438,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
   acc.val = rval;
   acc.rcp_tab = rcp_tab;
   acc.init_addresses();
-  acc.flags_sa = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable + kWarpsPerCta * 256) + (uint32_t)warp * (RING / 32) * 4u;
+  acc.flags_sa = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable + kLeanWarps * 256) + (uint32_t)warp * (RING / 32) * 4u;
   acc.no_flags = true;
   // GROUPED: per-warp "valid throughout" counters of the current group, one per 32-step word (behind everything else)
   uint32_t* const full_w = reinterpret_cast<uint32_t*>(smem_raw + lean_smem_bytes()) + warp * kLeanFullWords;
@@ -433,7 +446,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
     for (int i = lane; i < kLeanFullWords; i += 32) full_w[i] = 0u;
     __syncwarp();
   }
-  const uint32_t total_warps = gridDim.x * kWarpsPerCta;
+  const uint32_t total_warps = gridDim.x * kLeanWarps;
   const int32_t T = (int32_t)a.T;
   const long long tb_off = a.tb - a.offset;  // rel = ts + offset - tb
   const uint32_t step32 = 32u * (uint32_t)a.interval;
@@ -472,8 +485,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
     g_o = g; m_o = lo; e_o = hi;
     return g < a.g_hi;
   };
-  uint32_t s = blockIdx.x * kWarpsPerCta + warp;
+#if B2P_LEAN_CONTIG
+  // every CTA owns one contiguous range of series and its warps sweep it side by side: the SM's streams (ts, val, out)
+  // stay inside a few 2 MB pages at any time and move on together
+  const uint32_t per_cta = (a.n_series + gridDim.x - 1) / gridDim.x;
+  const uint32_t s_end = min(a.n_series, (blockIdx.x + 1u) * per_cta);
+  uint32_t s = blockIdx.x * per_cta + warp;
+  bool have = s < s_end;
+#else
+  const uint32_t s_end = a.n_series;
+  uint32_t s = blockIdx.x * kLeanWarps + warp;
   bool have = s < a.n_series;
+#endif
   if constexpr (GROUPED) {
     have = group_first(grp, m, m_end);
     if (have) s = a.g_members[m];
@@ -485,8 +508,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
     issue_block0(row0, row1);
   }
   while (have) {
+#if B2P_LEAN_CONTIG
+    uint32_t s_next = s + kLeanWarps;
+#else
     uint32_t s_next = s + total_warps;
-    bool have_next = s_next < a.n_series;
+#endif
+    bool have_next = s_next < s_end;
     if constexpr (GROUPED) {
       if (m + 1u < m_end) {
         grp_n = grp; m_n = m + 1u; m_end_n = m_end;
@@ -710,6 +737,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, B2P_LEAN_MIN_BLOCKS) range_
   cp_async_wait<0>();
 }
 
-__host__ __device__ constexpr size_t lean_grouped_smem_bytes() { return lean_smem_bytes() + (size_t)kWarpsPerCta * kLeanFullWords * 4; }
+__host__ __device__ constexpr size_t lean_grouped_smem_bytes() { return lean_smem_bytes() + (size_t)kLeanWarps * kLeanFullWords * 4; }
 
 }  // namespace b2p

@@ -80,11 +80,12 @@ int main(int argc, char** argv) {
   a.ts = ts; a.val = val; a.offsets = offsets; a.n_rows = n_rows; a.n_series = S; a.out = out; a.valid = valid;
   a.status = status; a.slow_list = slow_list; a.w_list = w_list; a.use_w_list = 0;
 #ifndef LAB_REF
-  a.b_list = nullptr; a.k0_status = status; a.sid_base = 0; a.sid_check = getenv("LAB_SID_CHECK") ? sid : nullptr;
+  a.b_list = nullptr;
 #endif
 
   auto kern = range_lean_kernel<LAB_FN, LAB_FLAGS>;
 #ifdef LAB_REF
+  constexpr int kLeanWarps = kWarpsPerCta;
   constexpr size_t smem = (size_t)kWarpsPerCta * kLeanRing * 16 + kRcpTable * 8 + (size_t)kWarpsPerCta * 2 * 64 * 16 +
                           (size_t)kWarpsPerCta * (kLeanRing / 32) * 4;
 #else
@@ -92,10 +93,10 @@ int main(int argc, char** argv) {
 #endif
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int nb = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWarpsPerCta * 32, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kLeanWarps * 32, smem));
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, kern));
-  const unsigned need = (S + kWarpsPerCta - 1) / kWarpsPerCta;
+  const unsigned need = (S + kLeanWarps - 1) / kLeanWarps;
   if (getenv("LAB_K2L_CTAS_PER_SM")) nb = atoi(getenv("LAB_K2L_CTAS_PER_SM"));
   const unsigned cap = 148u * (unsigned)(nb > 0 ? nb : 1);
   const unsigned grid = need < cap ? need : cap;
@@ -107,7 +108,7 @@ int main(int argc, char** argv) {
   };
   auto run_k2l = [&]() {
     cudaMemsetAsync(&status->w_count, 0, 4, st);
-    kern<<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    kern<<<grid, kLeanWarps * 32, smem, st>>>(a);
   };
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -125,7 +126,7 @@ int main(int argc, char** argv) {
   };
   const float ms_k0 = timeit(run_k0);
   const float ms_k2l = timeit(run_k2l);
-#if defined(LAB_OVERLAP) && !defined(LAB_REF)
+#if 0  /* K0 split experiment (search + validate kernels), dropped: see DESIGN.md */
   // K0 split: lower_bound search on the main stream, full-column validation on a side stream next to K2L
   cudaStream_t side;
   CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
@@ -184,9 +185,7 @@ int main(int argc, char** argv) {
     printf("   timeline (ms from step start): validate [%.3f, %.3f]  k2l [%.3f, %.3f]  end %.3f\n", v0, v1, k0_, k1_, te_);
   }
 #else
-  const float ms_step = a.sid_check ? timeit([&]() {
-    series_offsets_search_kernel<<<(S + 1 + 255) / 256, 256, 0, st>>>(sid, n_rows, S, 0u, offsets);
-    run_k2l(); }) : timeit([&]() { run_k0(); run_k2l(); });
+  const float ms_step = timeit([&]() { run_k0(); run_k2l(); });
 #endif
   Status hs;
   CK(cudaMemcpy(&hs, status, sizeof hs, cudaMemcpyDeviceToHost));

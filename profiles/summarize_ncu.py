@@ -1,5 +1,10 @@
 #!/usr/bin/env python
-"""Print the key raw-page metrics of every kernel launch in an .ncu-rep as a markdown table row set."""
+"""Print the key raw-page metrics of every kernel launch in an .ncu-rep as a markdown table row set.
+
+    summarize_ncu.py rep.ncu-rep [...]                       markdown on stdout
+    summarize_ncu.py --traffic-json OUT SAMPLES rep.ncu-rep  also write {kernel: dram bytes per input sample} (first
+                                                             launch of each kernel; SAMPLES = input samples per launch)
+bench.py reads profiles/r2_traffic.json written this way for roofline.traffic."""
 import csv
 import subprocess
 import sys
@@ -19,7 +24,12 @@ WANT = [
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu pipe %"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu pipe %"),
 ]
-for rep in sys.argv[1:]:
+args = sys.argv[1:]
+traffic_out, samples = None, None
+if args and args[0] == "--traffic-json":
+    traffic_out, samples, args = args[1], float(args[2]), args[3:]
+traffic = {}
+for rep in args:
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -37,3 +47,18 @@ for rep in sys.argv[1:]:
                     pass
                 cells.append(f"{label} {v} {units[i]}")
         print(f"- `{name}`: " + "; ".join(cells))
+        if traffic_out and "dram__bytes_read.sum" in hdr:
+            def gb(key):
+                i = hdr.index(key)
+                v, u = float(r[i]), units[i]
+                return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(u, 1.0)
+            full = r[hdr.index("Kernel Name")]
+            key = "range_lean_kernel_grouped" if ("range_lean_kernel" in full and full.rstrip(">)( RangeArgs").endswith("1")) else full.split("(")[0].split("<")[0].replace("void ", "").strip()
+            if key not in traffic:
+                b = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
+                traffic[key] = {"dram_bytes_per_launch": b, "dram_bytes_per_sample": b / samples,
+                                "samples_per_launch": samples, "kernel": full, "source": rep}
+if traffic_out:
+    import json
+    with open(traffic_out, "w") as f:
+        json.dump(traffic, f, indent=1)
