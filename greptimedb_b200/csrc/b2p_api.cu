@@ -161,6 +161,8 @@ struct b2p_ctx {
   Nccl::comm_t comm = nullptr;
   int comm_ranks = 1, comm_rank = 0;
   long long comm_headstart_cycles = 60000;  // ~30 us at 1.965 GHz (B2P_COMM_HEADSTART_US overrides)
+  int comm_reserve_sms = 8;                 // SMs the fused tier leaves to the tile all-reduce (B2P_COMM_RESERVE_SMS)
+  int comm_reserve_now = 0;                 // ... in effect for the launch being issued
   cudaStream_t s_comm = nullptr;
   cudaEvent_t ev_comm_in = nullptr, ev_comm_done = nullptr, ev_comm_go = nullptr;
   DevBuf m_tmp0, m_tmp1;             // scratch of the variance merge
@@ -374,7 +376,10 @@ int launch_lean_grouped(b2p_ctx* c, const RangeArgs& a) {
   }
   const unsigned n_g = a.g_hi - a.g_lo;
   const unsigned need = (n_g + kLeanWarps - 1) / kLeanWarps;
-  const unsigned cap = (unsigned)(c->num_sms * cached);
+  // The grid is one CTA per SM and takes its groups from a counter, so it can be any size: while tiles are being
+  // all-reduced a few SMs are left to the collective's CTAs (they cannot be placed beside a resident 24-warp CTA).
+  unsigned cap = (unsigned)(c->num_sms * cached);
+  if (c->comm_reserve_now > 0 && cap > (unsigned)c->comm_reserve_now + 8u) cap -= (unsigned)c->comm_reserve_now;
   const unsigned grid = need < cap ? need : cap;
   if (grid == 0) return B2P_OK;
   kern<<<grid, kLeanWarps * 32, smem, c->stream>>>(a);
@@ -565,6 +570,7 @@ b2p_ctx* b2p_create(int device) {
   if (const char* e = getenv("B2P_DISABLE_LEAN_TIER")) c->lean_tier = !(e[0] == '1');
   if (const char* e = getenv("B2P_LEAN_ADAPTIVE")) c->lean_adaptive = !(e[0] == '0');
   if (const char* e = getenv("B2P_LEAN_FORCE_FLAGS")) c->lean_force_flags = (e[0] == '1');
+  if (const char* e = getenv("B2P_COMM_RESERVE_SMS")) c->comm_reserve_sms = atoi(e);
   if (const char* e = getenv("B2P_COMM_HEADSTART_US")) c->comm_headstart_cycles = (long long)(atof(e) * 1965.0);
   if (const char* e = getenv("B2P_ARENA_ROWS")) c->arena_rows_wanted = (size_t)strtoull(e, nullptr, 10);
   return c;
@@ -887,6 +893,7 @@ static int range_call(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, 
     if (!c->comm && c->comm_ranks > 1) return fail(B2P_E_INVALID, "no communicator: call b2p_comm_init first");
     const uint32_t n_t = (uint32_t)gt->allreduce_tiles;
     const uint64_t span = (uint64_t)gt->g_hi - gt->g_lo;
+    c->comm_reserve_now = (c->comm && n_t > 1) ? c->comm_reserve_sms : 0;
     for (uint32_t t = 0; t < n_t; ++t) {
       a.g_lo = gt->g_lo + (uint32_t)(span * t / n_t);
       a.g_hi = gt->g_lo + (uint32_t)(span * (t + 1) / n_t);
@@ -912,6 +919,7 @@ static int range_call(b2p_ctx* c, const b2p_range_params* p, const int64_t* ts, 
         stage_end_on(c, 4, c->s_comm);
       }
     }
+    c->comm_reserve_now = 0;
     if (c->comm) {  // everything after this call on the context's stream sees the merged partials
       CU(cudaEventRecord(c->ev_comm_done, c->s_comm));
       CU(cudaStreamWaitEvent(c->stream, c->ev_comm_done, 0));

@@ -53,7 +53,10 @@ for rep in args:
                 v, u = float(r[i]), units[i]
                 return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(u, 1.0)
             full = r[hdr.index("Kernel Name")]
-            key = "range_lean_kernel_grouped" if ("range_lean_kernel" in full and full.rstrip(">)( RangeArgs").endswith("1")) else full.split("(")[0].split("<")[0].replace("void ", "").strip()
+            plain = full.replace("(bool)", "").replace("(int)", "").replace("b2p::", "")
+            key = plain.split("(")[0].split("<")[0].replace("void ", "").strip()
+            if key == "range_lean_kernel" and plain.split(">")[0].rstrip().endswith("1"):
+                key = "range_lean_kernel_grouped"  # template <FN, FLAGS, GROUPED>
             if key not in traffic:
                 b = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
                 traffic[key] = {"dram_bytes_per_launch": b, "dram_bytes_per_sample": b / samples,
