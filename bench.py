@@ -56,13 +56,13 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def load_traffic():
+def load_traffic(key="range_lean_kernel"):
     """dram__bytes_read.sum + dram__bytes_write.sum per input sample of the dominant kernel, from the committed ncu
     --set full capture of the shipped kernel (profiles/r2_traffic.json, written by profiles/summarize_ncu.py)."""
     try:
         with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             d = json.load(f)
-        return float(d["range_lean_kernel"]["dram_bytes_per_sample"]), d["range_lean_kernel"].get("source", "profiles/r2_traffic.json")
+        return float(d[key]["dram_bytes_per_sample"]), f"profiles/r2_traffic.json[{key}] ({d[key].get('kernel', '')})"
     except Exception:
         return None, None
 
@@ -146,12 +146,15 @@ def query_params(n_samples=N_SAMPLES):
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm (oracle port of the reference's CPU path; test infrastructure timed as the reported baseline)
 # ---------------------------------------------------------------------------------------------------------------
+JITTER_MS = 0  # set from --jitter-ms
+
+
 def cpu_reference_pass(n_series: int, threads: int, faithful: bool = True, series_begin: int = 0, with_resets=0,
                        n_samples: int = N_SAMPLES):
     """One pass of the reference's CPU algorithm (oracle port, structure-faithful) -> (seconds, samples, out, valid)."""
     import numpy as np
     from oracle import oracle as orc
-    ts, val, sid = orc.synth_fill(series_begin, n_series, n_samples, T0, SCRAPE, 1000, with_resets, SEED)
+    ts, val, sid = orc.synth_fill(series_begin, n_series, n_samples, T0, SCRAPE, JITTER_MS, with_resets, SEED)
     offsets = np.arange(n_series + 1, dtype=np.uint64) * n_samples
     p = orc.make_params("rate", T0, T0 + (n_samples - 1) * SCRAPE, SCRAPE, RANGE)
     t = time.perf_counter()
@@ -373,19 +376,30 @@ def bench_config2(h: Harness, sampler):
     out = torch.empty(S * T, dtype=torch.float64, device=dev)
     valid = torch.empty(S * Tw, dtype=torch.int32, device=dev)
     # series are hash-sharded across GPUs: rank r owns global series [r*S, (r+1)*S) of this step's chunk
-    ctx.synth_fill_dev(h.rank * S, S, N_SAMPLES, T0, SCRAPE, 1000, args.resets, SEED, ts, val, sid)
-    ctx.sync()
-
     def step():
         ctx.series_offsets_dev(sid, n_rows, S, offsets)
         ctx.range_eval_dev(p, ts, val, offsets, n_rows, S, out, valid)
+
+    # the scrape-jitter variant of the generator (timestamps +< 1 s off the schedule; the
+    # round-1 headline workload), measured the same way before the headline so that the resident data is the headline's
+    jitter_variant = None
+    if args.jitter_variant_ms > 0 and args.jitter_variant_ms != args.jitter_ms:
+        ctx.synth_fill_dev(h.rank * S, S, N_SAMPLES, T0, SCRAPE, args.jitter_variant_ms, args.resets, SEED, ts, val, sid)
+        ctx.sync()
+        jms, _, _ = h.timed(step, args.steps, args.warmup)
+        jitter_variant = {"jitter_ms": args.jitter_variant_ms, "ms_per_step": jms,
+                          "value": n_rows * h.world / (jms * 1e-3), "unit": UNIT,
+                          "warp_tier_series": ctx.last_warp_tier_series(), "slow_path_series": ctx.last_slow_series()}
+    ctx.synth_fill_dev(h.rank * S, S, N_SAMPLES, T0, SCRAPE, args.jitter_ms, args.resets, SEED, ts, val, sid)
+    ctx.sync()
 
     ms, launches, window = h.timed(step, args.steps, args.warmup)
     slow_series, warp_tier_series = ctx.last_slow_series(), ctx.last_warp_tier_series()
     clocks = sampler.stop(*window) if sampler else None
     st = h.stage_ms(step, (0, 1), reps=min(args.steps, 5))
     res = {"S": S, "n_rows": n_rows, "T": T, "Tw": Tw, "ms": ms, "launches": launches, "clocks": clocks,
-           "k0_ms": st[0], "k2_ms": st[1], "slow_series": slow_series, "warp_tier_series": warp_tier_series}
+           "k0_ms": st[0], "k2_ms": st[1], "slow_series": slow_series, "warp_tier_series": warp_tier_series,
+           "jitter_variant": jitter_variant}
 
     # ---- end to end through the host-pointer C ABI: pinned host buffers, H2D + kernels + D2H timed ----
     Se = args.e2e_series
@@ -455,7 +469,7 @@ def bench_config3(h: Harness):
     val = torch.empty(n_rows, dtype=torch.float64, device=dev)
     sid = torch.empty(n_rows, dtype=torch.int32, device=dev)
     offsets = torch.empty(S + 1, dtype=torch.int64, device=dev)
-    ctx.synth_fill_dev(h.rank * S, S, N_SAMPLES, T0, SCRAPE, 1000, args.resets, SEED, ts, val, sid)
+    ctx.synth_fill_dev(h.rank * S, S, N_SAMPLES, T0, SCRAPE, args.jitter_ms, args.resets, SEED, ts, val, sid)
     gid_np = (D.mix32(np.arange(h.rank * S, (h.rank + 1) * S, dtype=np.uint32)) % np.uint32(G)).astype(np.int32)
     gid = torch.from_numpy(gid_np).to(dev)
     gsum = torch.zeros(G * T, dtype=torch.float64, device=dev)
@@ -524,7 +538,7 @@ def bench_config4(h: Harness):
     ts = torch.empty(n_rows, dtype=torch.int64, device=dev)
     val = torch.empty(n_rows, dtype=torch.float64, device=dev)
     sid = torch.empty(n_rows, dtype=torch.int32, device=dev)
-    ctx.synth_fill_dev(h.rank * S, S, N, T0, SCRAPE, 1000, 0, SEED, ts, val, sid)
+    ctx.synth_fill_dev(h.rank * S, S, N, T0, SCRAPE, args.jitter_ms, 0, SEED, ts, val, sid)
     ctx.sync()
     torch.cuda.synchronize()
     # cumulative histogram: bucket b counts everything below le[b] -> prefix sum over the bucket axis
@@ -640,17 +654,24 @@ def run_ours(args):
     elif lean_on and args.resets:
         kernel_name = ("range_lean_kernel<rate, bit words> (adaptive: the plain variant handed off every series during the "
                        "warm-up) + range_fast_kernel<rate> over the series it hands off")
+    elif lean_on and args.jitter_ms == 0 and os.environ.get("B2P_UNIFORM", "") != "0":
+        kernel_name = ("range_lean_kernel<rate, uniform cadence> (picked by cadence_probe_kernel: samples exactly one eval "
+                       "interval apart) + range_fast_kernel<rate> over the series it hands off")
     else:
         kernel_name = ("range_lean_kernel<rate> (+ range_fast_kernel<rate> over the series it hands off)" if lean_on
                        else "range_fast_kernel<rate>")
-    per_sample, traffic_src = load_traffic()
+    uniform = lean_on and not args.resets and args.jitter_ms == 0 and os.environ.get("B2P_UNIFORM", "") != "0"
+    per_sample, traffic_src = load_traffic("range_lean_kernel_uniform" if uniform else "range_lean_kernel")
     value = S * N_SAMPLES * h.world / (step_ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": h.world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"rate(x[5m]) step 15s over {S} series x {N_SAMPLES} samples per GPU per step "
-                               f"(BASELINE config 2 = 10M series processed as chunks of {S}); resets={args.resets}",
+                               f"(BASELINE config 2 = 10M series processed as chunks of {S}); resets={args.resets}; "
+                               + ("scrapes on the 15 s schedule (BASELINE.md section 4 main shape)" if args.jitter_ms == 0
+                                  else f"scrape timestamps +<{args.jitter_ms} ms off the schedule (BASELINE.md section 4 variant)"),
+                   "scrape_jitter_ms": args.jitter_ms,
                    "series_per_gpu_per_step": S, "samples_per_series": N_SAMPLES, "eval_steps": T,
                    "parallelism": f"series-sharded x{h.world}, no data-path collective in config 2 "
                                   "(configs.3 / configs.5 carry the collectives)",
@@ -666,6 +687,11 @@ def run_ours(args):
         "gpu_launches": c2["launches"], "slow_path_series": c2["slow_series"], "warp_tier_series": c2["warp_tier_series"],
         "clocks": c2["clocks"],
     }
+    if c2["jitter_variant"]:
+        # the same step over the generator's jittered timestamps (round 1's headline workload): the general first tier
+        jv = dict(c2["jitter_variant"])
+        jv["hbm_read_frac_whole_step"] = 20.0 * n_rows / (jv["ms_per_step"] * 1e-3) / 1e9 / peak
+        line["jitter_variant"] = jv
     if c2["e2e"]:
         line["e2e"] = c2["e2e"]
     cores = os.cpu_count() or 1
@@ -698,6 +724,11 @@ def main():
     ap.add_argument("--series-per-gpu", type=int, default=1_250_000)
     ap.add_argument("--e2e-series", type=int, default=131_072)
     ap.add_argument("--resets", type=int, default=0, help="1 = counter-reset variant of the value generator")
+    ap.add_argument("--jitter-ms", type=int, default=0,
+                    help="scrape jitter of the generator: 0 = timestamps on the schedule (BASELINE.md section 4, main shape), "
+                         "1000 = the +<1 s variant (round 1's headline)")
+    ap.add_argument("--jitter-variant-ms", type=int, default=1000,
+                    help="config 2 is measured a second time with this jitter and reported as configs['2'].jitter_variant (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="all", choices=["all", "rate", "sumby", "hist", "wide"],
                     help="all = config 2 (headline) + configs 3, 4, 5 in `configs`; rate = config 2 only; "
@@ -708,6 +739,8 @@ def main():
     ap.add_argument("--hist-per-gpu", type=int, default=125_000)
     ap.add_argument("--wide-rows-per-gpu", type=int, default=12_500_000)
     args = ap.parse_args()
+    global JITTER_MS
+    JITTER_MS = args.jitter_ms
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -185,7 +185,10 @@ struct b2p_ctx {
   int last_range_fn = 0;
   bool last_used_lean = false;  // the pending / last range call started with K2L
   uint32_t last_range_series = 0;
-  int lean_blocks_per_sm[B2P_FN__COUNT][2] = {};
+  int lean_blocks_per_sm[B2P_FN__COUNT][2][2] = {};  // [fn][FLAGS][UNI]
+  // first-tier variant for equally spaced samples (rate / increase / delta): -1 = cadence_probe_kernel decides per call
+  // on the device, 0 / 1 = forced (B2P_UNIFORM)
+  int uniform_mode = -1;
   size_t arena_rows = 0;
   size_t arena_rows_wanted = 0;  // B2P_ARENA_ROWS: initial size of the slow-path arena (default kArenaDefaultRows)
   cudaEvent_t ev[5][2] = {};  // 0 K0, 1 range tiers, 2 slow kernel, 3 by-label aggregate, 4 all-reduce (last tile)
@@ -324,11 +327,24 @@ int launch_fast(b2p_ctx* c, const RangeArgs& a) {
 // ends of the 31 steps past the grid still below the 0xFFFFFFFF end sentinel.
 bool lean_ok(const b2p_ctx* c, int fn, const RangeArgs& a);
 
-template <int FN, bool FLAGS>
-int launch_lean(b2p_ctx* c, const RangeArgs& a) {
+// Functions whose first tier has a uniform-cadence variant: the probe (or B2P_UNIFORM) writes Status::uniform, then
+// both variants are launched and the one the verdict does not name returns at once — no host round trip.
+static int cadence_verdict(b2p_ctx* c, const RangeArgs& a) {
+  if (c->uniform_mode < 0) {
+    cadence_probe_kernel<<<1, kProbeThreads, 0, c->stream>>>(a);
+    c->launches++;
+    CU(cudaGetLastError());
+  } else {
+    CU(cudaMemsetAsync(&a.status->uniform, c->uniform_mode ? 1 : 0, sizeof(uint32_t), c->stream));
+  }
+  return B2P_OK;
+}
+
+template <int FN, bool FLAGS, bool UNI>
+int launch_lean_variant(b2p_ctx* c, const RangeArgs& a) {
   constexpr size_t smem = lean_smem_bytes();
-  auto kern = range_lean_kernel<FN, FLAGS>;
-  int& cached = c->lean_blocks_per_sm[FN][FLAGS ? 1 : 0];
+  auto kern = range_lean_kernel<FN, FLAGS, false, UNI>;
+  int& cached = c->lean_blocks_per_sm[FN][FLAGS ? 1 : 0][UNI ? 1 : 0];
   if (cached == 0) {
     int nb = 0;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -343,6 +359,18 @@ int launch_lean(b2p_ctx* c, const RangeArgs& a) {
   c->launches++;
   CU(cudaGetLastError());
   return B2P_OK;
+}
+
+template <int FN, bool FLAGS>
+int launch_lean(b2p_ctx* c, const RangeArgs& a) {
+  if constexpr (kLeanUniform<FN, FLAGS>) {
+    int rc = cadence_verdict(c, a);
+    if (!rc && c->uniform_mode != 0) rc = launch_lean_variant<FN, FLAGS, true>(c, a);
+    if (!rc && c->uniform_mode != 1) rc = launch_lean_variant<FN, FLAGS, false>(c, a);
+    return rc;
+  } else {
+    return launch_lean_variant<FN, FLAGS, false>(c, a);
+  }
 }
 
 // `with_flags`: the variant whose ring carries the reset / change bit words (always for resets() / changes(); for
@@ -362,10 +390,10 @@ int launch_lean_if_supported(b2p_ctx* c, const RangeArgs& a, bool with_flags) {
 
 // First tier of the fused by-label SUM: rate / increase / delta walk the series group by group and add into
 // gsum / gcnt (range_lean_kernel<FN, FLAGS, GROUPED = true>).
-template <int FN, bool FLAGS>
-int launch_lean_grouped(b2p_ctx* c, const RangeArgs& a) {
+template <int FN, bool FLAGS, bool UNI>
+int launch_lean_grouped_variant(b2p_ctx* c, const RangeArgs& a) {
   constexpr size_t smem = lean_grouped_smem_bytes();
-  auto kern = range_lean_kernel<FN, FLAGS, true>;
+  auto kern = range_lean_kernel<FN, FLAGS, true, UNI>;
   static int cached_nb[16] = {};  // per device
   int& cached = cached_nb[c->device & 15];
   if (cached == 0) {
@@ -386,6 +414,17 @@ int launch_lean_grouped(b2p_ctx* c, const RangeArgs& a) {
   c->launches++;
   CU(cudaGetLastError());
   return B2P_OK;
+}
+template <int FN, bool FLAGS>
+int launch_lean_grouped(b2p_ctx* c, const RangeArgs& a) {
+  if constexpr (kLeanUniform<FN, FLAGS>) {
+    int rc = cadence_verdict(c, a);
+    if (!rc && c->uniform_mode != 0) rc = launch_lean_grouped_variant<FN, FLAGS, true>(c, a);
+    if (!rc && c->uniform_mode != 1) rc = launch_lean_grouped_variant<FN, FLAGS, false>(c, a);
+    return rc;
+  } else {
+    return launch_lean_grouped_variant<FN, FLAGS, false>(c, a);
+  }
 }
 bool lean_grouped_fn(int fn) { return fn == B2P_FN_RATE || fn == B2P_FN_INCREASE || fn == B2P_FN_DELTA; }
 int dispatch_lean_grouped(b2p_ctx* c, int fn, const RangeArgs& a, bool with_flags) {
@@ -570,6 +609,7 @@ b2p_ctx* b2p_create(int device) {
   if (const char* e = getenv("B2P_DISABLE_LEAN_TIER")) c->lean_tier = !(e[0] == '1');
   if (const char* e = getenv("B2P_LEAN_ADAPTIVE")) c->lean_adaptive = !(e[0] == '0');
   if (const char* e = getenv("B2P_LEAN_FORCE_FLAGS")) c->lean_force_flags = (e[0] == '1');
+  if (const char* e = getenv("B2P_UNIFORM")) c->uniform_mode = (e[0] == '0') ? 0 : (e[0] == '1' ? 1 : -1);
   if (const char* e = getenv("B2P_COMM_RESERVE_SMS")) c->comm_reserve_sms = atoi(e);
   if (const char* e = getenv("B2P_COMM_HEADSTART_US")) c->comm_headstart_cycles = (long long)(atof(e) * 1965.0);
   if (const char* e = getenv("B2P_ARENA_ROWS")) c->arena_rows_wanted = (size_t)strtoull(e, nullptr, 10);

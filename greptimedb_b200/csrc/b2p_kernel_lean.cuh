@@ -50,16 +50,21 @@ constexpr int kLeanRing = 256;
 #define B2P_LEAN_WARPS 24
 #endif
 constexpr int kLeanWarps = B2P_LEAN_WARPS;
+// 64-row blocks of a warp's staging area: the block being consumed plus kLeanDepth - 1 in flight (cp.async groups)
+#ifndef B2P_LEAN_DEPTH
+#define B2P_LEAN_DEPTH 2
+#endif
+constexpr int kLeanDepth = B2P_LEAN_DEPTH;
 // dynamic shared memory of one CTA: value ring + mirrored timestamp ring + reciprocal table + staging (two 64-row
-// blocks per warp and column) + bit words
+// blocks per warp and column) + bit words + per-warp window-shape cache of the uniform-cadence path (32 B)
 // GROUPED (fused by-label partials): per-warp counters "members of the current group whose 32-step word k/32 was valid
 // throughout" — the by far most common word; they are added to the count row when the warp leaves the group, so the
 // hot path updates the per-step counts in global memory only for the few partially valid words
 constexpr int kLeanFullWords = 256;  // => T <= 8192 eval steps on the fused path (host gate)
 __host__ __device__ constexpr size_t lean_grouped_smem_bytes();
 __host__ __device__ constexpr size_t lean_smem_bytes() {
-  return (size_t)kLeanWarps * kLeanRing * 16 + kRcpTable * 8 + (size_t)kLeanWarps * 2 * 64 * 16 +
-         (size_t)kLeanWarps * (kLeanRing / 32) * 4;
+  return (size_t)kLeanWarps * kLeanRing * 16 + kRcpTable * 8 + (size_t)kLeanWarps * kLeanDepth * 64 * 16 +
+         (size_t)kLeanWarps * (kLeanRing / 32) * 4 + (size_t)kLeanWarps * 32;
 }
 
 // The per-warp sample ring of this tier.  Timestamps (uint32 ms since start - range) are stored twice, slot p
@@ -82,6 +87,8 @@ struct LeanRingT {
   uint32_t flags_sa;       // [RING/32] bit words (FLAGS only)
   bool no_flags;           // warp-uniform hint: no set bit can lie inside any window of this group
   uint32_t lin_sa;         // ts_sa + 4 * ((j0 & (RING-1)) - j0)
+  // uniform-cadence path: {f64 factor; u32 to_end, to_start, length, far} of the window shape last seen by this warp
+  uint32_t shape_sa;
   __device__ __forceinline__ void init_addresses() {
     ts_sa = (uint32_t)__cvta_generic_to_shared(ts);
     val_sa = (uint32_t)__cvta_generic_to_shared(val);
@@ -152,6 +159,9 @@ struct LeanState {  // warp-uniform
   // would hit the overshoot quirk
   uint32_t phase;
   uint32_t last_flag;  // FLAGS variant: ordinal of the newest set reset / change bit (0 = none yet)
+  // samples [reg_from, j_cnt) are exactly one eval interval apart from each other (tracked block by block while they
+  // are appended): windows over them all have the same shape, see lean_pair
+  uint32_t reg_from;
 };
 
 // The value of one step whose window [q, g] (both edge timestamps known) is already established.
@@ -305,83 +315,203 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Lea
 #ifndef B2P_LEAN_PAIR
 #define B2P_LEAN_PAIR 1
 #endif
+#ifndef B2P_LEAN_UNIFORM
+#define B2P_LEAN_UNIFORM 1
+#endif
+
+// The uniform-cadence path is compiled into the plain variants of the extrapolated functions (rate / increase / delta):
+// there the per-step arithmetic it removes dominates.  (With the reset bit words the correction scan dominates, and the
+// *_over_time functions walk their windows anyway: measured, no gain.)
+// It is a kernel variant of its own (template parameter UNI) — compiled into the general kernel it costs the jittered
+// case 6 % through register pressure — and cadence_probe_kernel picks one of the two per call on the device.
+template <int FN, bool FLAGS>
+constexpr bool kLeanUniform = B2P_LEAN_UNIFORM && !FLAGS && FnTraits<FN>::kExtrapolated;
+
+// The window shape of a run of equally spaced samples evaluated at a step equal to their spacing: every window is the
+// previous one moved on by one sample, so its length and the distances of its edge samples to the window edges repeat.
+struct LeanShape {
+  uint32_t to_end, to_start, len;  // te - t[hi], t[lo] - (te - range), hi - lo + 1
+  bool far;                        // (t[hi] - t[lo]) >= to_start, the value-independent half of extrapolate_parts' shortcut
+  double factor;                   // extrapolate_factor of the shape with to_start unchanged (extrapolated functions)
+};
+
+// A step of such a run.  Extrapolated functions: whenever ExtrapolatedRate::calc leaves to_start alone (no counter, no
+// positive increase, or the zero crossing provably outside the window: the same exact shortcut as extrapolate_parts)
+// the value is result * factor with the factor of the shape — the identical sequence of operations on identical
+// operands, evaluated once per shape instead of once per step; any other step takes extrapolate_parts itself.
+template <int FN, bool FLAGS>
+__device__ __forceinline__ double lean_value_shape(const RangeArgs& a, const LeanRingT<FLAGS>& acc, int32_t g, uint32_t q,
+                                                   uint32_t te, const LeanShape& sh, bool& ok) {
+  using TR = FnTraits<FN>;
+  const uint32_t t_hi = te - sh.to_end, t_lo = te - (uint32_t)a.range + sh.to_start;
+  if constexpr (TR::kExtrapolated) {
+    ok = sh.len >= 2u;
+    double r = 0.0;
+    if (ok) {
+      const double first_value = acc.v(q);
+      const double last_value = acc.v((uint32_t)g);
+      double result_value = last_value - first_value;
+      if constexpr (TR::kCounter) result_value += FLAGS ? reset_correction(acc, q, (uint32_t)g) : 0.0;
+      bool plain = true;
+      if constexpr (TR::kCounter)
+        plain = !(result_value > 0.0 && first_value >= 0.0) || (B2P_LEAN_FAR && sh.far && first_value >= result_value);
+      if (plain)
+        r = result_value * sh.factor;
+      else
+        r = extrapolate_parts<FN, uint32_t, true>(result_value, first_value, t_lo, t_hi, sh.len, te, (uint32_t)a.range,
+                                                  acc.rcp(sh.len - 1u), a.range_secs, a.rcp_rs);
+    }
+    return r;
+  } else {
+    return lean_value<FN, FLAGS>(a, acc, g, q, t_lo, t_hi, te, ok);
+  }
+}
 
 // Two consecutive groups (64 steps) in one go, steady state only: before the end of the stream, previous step
 // non-empty, at most one sample of advance per step (so no cursor start can reach m, see lean_group), and every
 // one of the 64 proportional guesses verified by one vote.  Returns false without side effects when any of that
 // does not hold; the caller then takes the groups one at a time.
-template <int FN, bool FLAGS, bool GROUPED = false>
+//
+// Uniform cadence (B2P_LEAN_UNIFORM): when every sample from the one before the previous step's window up to the one
+// after the last of these 64 windows is exactly one eval interval after its predecessor (LeanState::reg_from, checked
+// once per sample while the block is appended), step k's window is step k-1's moved on by one sample:
+//   t[lo-1] <= tlo < t[lo] and t[hi] <= te < t[hi+1]   =>   t[lo] <= tlo + iv < t[lo+1] and t[hi+1] <= te + iv < t[hi+2].
+// The edges of all 64 windows follow from the previous step's without a single verification read, all windows have
+// the previous one's shape, and the cursor start of calculate_range is lo - 1 + 1 <= hi < m.  This is the layout of
+// aligned scrapes (Prometheus aligns scrape timestamps to the schedule; the BASELINE generator without jitter).
+template <int FN, bool FLAGS, bool GROUPED = false, bool UNI = false>
 __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, LeanRingT<FLAGS>& acc, uint32_t te,
                                           uint32_t step32, double* out_p, uint32_t* vw_p, int lane,
                                           uint32_t* full_p = nullptr) {
+  using TR = FnTraits<FN>;
   const int32_t top = (int32_t)st.j_cnt - 1;
-  // uniform gates; the last two keep every read below the newest sample (slot top), i.e. on written slots
-  if (st.phase != 1u || st.d_lo > 32u || st.base_hi + 2 * (int32_t)st.d_hi >= top || st.base_lo + 2u * st.d_lo > (uint32_t)top)
-    return false;
+  if (st.phase != 1u) return false;
   const uint32_t rng = (uint32_t)a.range;
   const uint32_t lane1 = (uint32_t)lane + 1u;
   const uint32_t te_b = te + step32;
-  const uint32_t tlo_a = te - rng, tlo_b = te_b - rng;
-  acc.set_window((int32_t)st.base_lo - 1);
   if constexpr (FLAGS) acc.no_flags = st.last_flag <= st.base_lo;  // no bit can lie inside a window of this group
-  int32_t g_a = st.base_hi + (int32_t)((lane1 * st.d_hi) >> 5), g_b = g_a + (int32_t)st.d_hi;
-  uint32_t q_a = st.base_lo + ((lane1 * st.d_lo) >> 5), q_b = q_a + st.d_lo;
-  uint32_t t_hi_a = acc.t((uint32_t)g_a);
-  const uint32_t t_hi1_a = acc.t((uint32_t)(g_a + 1));
-  const uint32_t t_lo1_a = acc.t(q_a - 1u);
-  uint32_t t_lo_a = acc.t(q_a);
-  uint32_t t_hi_b = acc.t((uint32_t)g_b);
-  const uint32_t t_hi1_b = acc.t((uint32_t)(g_b + 1));
-  const uint32_t t_lo1_b = acc.t(q_b - 1u);
-  uint32_t t_lo_b = acc.t(q_b);
-  const bool good = (t_hi_a <= te) && (t_hi1_a > te) && (t_lo1_a <= tlo_a) && (t_lo_a > tlo_a) && ((int32_t)q_a <= g_a) &&
-                    (t_hi_b <= te_b) && (t_hi1_b > te_b) && (t_lo1_b <= tlo_b) && (t_lo_b > tlo_b) && ((int32_t)q_b <= g_b);
-  if (__all_sync(0xffffffffu, good)) {
-    st.base_hi += 2 * (int32_t)st.d_hi;
-    st.base_lo += 2u * st.d_lo;
-  } else {
-    // Repair in place (the usual miss: a sample exactly on a window edge shifts a few guesses by one): every lane
-    // walks both steps to their definitional edges — the newest sample is younger than both window ends and slot
-    // base_lo - 1 / the -1 sentinel bound the walks — and the pair goes on if the short form of lean_group holds
-    // for all 64 steps (non-empty windows, at most two samples of advance per step => every cursor start is
-    // <= lo + 1 <= top < m).  Nothing of the warp state has been touched yet, so "false" still means "one at a time".
-    while (acc.t((uint32_t)(g_a + 1)) <= te) ++g_a;
-    while (acc.t((uint32_t)g_a) > te) --g_a;
-    q_a = q_a > (uint32_t)(g_a + 1) ? (uint32_t)(g_a + 1) : q_a;
-    while (acc.t(q_a - 1u) > tlo_a) --q_a;
-    while (acc.t(q_a) <= tlo_a) ++q_a;
-    while (acc.t((uint32_t)(g_b + 1)) <= te_b) ++g_b;
-    while (acc.t((uint32_t)g_b) > te_b) --g_b;
-    q_b = q_b > (uint32_t)(g_b + 1) ? (uint32_t)(g_b + 1) : q_b;
-    while (acc.t(q_b - 1u) > tlo_b) --q_b;
-    while (acc.t(q_b) <= tlo_b) ++q_b;
-    uint32_t prev_a = __shfl_up_sync(0xffffffffu, q_a, 1);
-    uint32_t prev_b = __shfl_up_sync(0xffffffffu, q_b, 1);
-    const uint32_t last_a = __shfl_sync(0xffffffffu, q_a, 31);
-    if (lane == 0) {
-      prev_a = st.base_lo;
-      prev_b = last_a;
-    }
-    const bool fine = ((int32_t)q_a <= g_a) && ((int32_t)q_b <= g_b) && (q_a - prev_a <= 2u) && (q_b - prev_b <= 2u);
-    if (!__all_sync(0xffffffffu, fine)) return false;
-    t_hi_a = acc.t((uint32_t)g_a);
-    t_lo_a = acc.t(q_a);
-    t_hi_b = acc.t((uint32_t)g_b);
-    t_lo_b = acc.t(q_b);
-    const int32_t nhi = __shfl_sync(0xffffffffu, g_b, 31);
-    const uint32_t nlo = __shfl_sync(0xffffffffu, q_b, 31);
-    st.d_hi = (uint32_t)(nhi - st.base_hi + 1) >> 1;  // advance per group over the 64 steps
-    st.d_lo = (nlo - st.base_lo + 1u) >> 1;
-    st.base_hi = nhi;
-    st.base_lo = nlo;
-  }
+  int32_t g_a, g_b;
+  uint32_t q_a, q_b;
   bool ok_a, ok_b;
+  double r_a, r_b;
+  [[maybe_unused]] double s_a = 0.0, s_b = 0.0;
+  // (reg_from < base_lo: the sample before the previous window is part of the run; base_hi + 65 <= top: so is the one
+  // after the last window, and all of them have been appended)
+  const bool uniform = UNI && st.reg_from < st.base_lo && st.base_hi + 65 <= top;
+  if (uniform) {
+    const uint32_t te_prev = te - lane1 * (uint32_t)a.interval;  // window end of the previous step
+    const uint32_t t_hi_p = acc.tm((uint32_t)st.base_hi), t_lo_p = acc.tm(st.base_lo);
+    LeanShape sh;
+    sh.to_end = te_prev - t_hi_p;
+    sh.to_start = t_lo_p - (te_prev - rng);
+    sh.len = (uint32_t)st.base_hi - st.base_lo + 1u;
+    sh.far = false;
+    sh.factor = 0.0;
+    if constexpr (TR::kExtrapolated) {
+      // factor of this shape: per-warp cache of the last shape (a series keeps one shape over its run)
+      uint32_t k0, k1, k2, k3;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(k0), "=r"(k1), "=r"(k2), "=r"(k3) : "r"(acc.shape_sa + 16u) : "memory");
+      if (k0 == sh.to_end && k1 == sh.to_start && k2 == sh.len) {
+        sh.factor = LeanRingT<FLAGS>::lds64(acc.shape_sa);
+        sh.far = k3 != 0u;
+      } else {
+        const uint32_t sampled_i = t_hi_p - t_lo_p;
+        sh.far = sampled_i >= sh.to_start;
+        if (sh.len >= 2u) {
+          const double sampled = (double)sampled_i;
+          const double average = div_by_rcp(sampled, (double)(sh.len - 1u), acc.rcp(sh.len - 1u));
+          sh.factor = extrapolate_factor<FN, true>(sampled, average, (double)sh.to_start, (double)sh.to_end, a.range_secs, a.rcp_rs);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          sts64(acc.shape_sa, sh.factor);
+          sts32(acc.shape_sa + 16u, sh.to_end);
+          sts32(acc.shape_sa + 20u, sh.to_start);
+          sts32(acc.shape_sa + 24u, sh.len);
+          sts32(acc.shape_sa + 28u, sh.far ? 1u : 0u);
+        }
+        __syncwarp();
+      }
+    }
+    g_a = st.base_hi + (int32_t)lane1;
+    g_b = g_a + 32;
+    q_a = st.base_lo + lane1;
+    q_b = q_a + 32u;
+    st.base_hi += 64;
+    st.base_lo += 64u;
+    st.d_hi = 32u;
+    st.d_lo = 32u;
+    if constexpr (GROUPED) { s_a = out_p[0]; s_b = out_p[32]; }  // the running partials are requested before the values
+    r_a = lean_value_shape<FN, FLAGS>(a, acc, g_a, q_a, te, sh, ok_a);
+    if constexpr (!GROUPED) out_p[0] = r_a;
+    r_b = lean_value_shape<FN, FLAGS>(a, acc, g_b, q_b, te_b, sh, ok_b);
+    if constexpr (!GROUPED) out_p[32] = r_b;
+  } else {
+    // uniform gates; the last two keep every read below the newest sample (slot top), i.e. on written slots
+    if (st.d_lo > 32u || st.base_hi + 2 * (int32_t)st.d_hi >= top || st.base_lo + 2u * st.d_lo > (uint32_t)top) return false;
+    const uint32_t tlo_a = te - rng, tlo_b = te_b - rng;
+    acc.set_window((int32_t)st.base_lo - 1);
+    g_a = st.base_hi + (int32_t)((lane1 * st.d_hi) >> 5);
+    g_b = g_a + (int32_t)st.d_hi;
+    q_a = st.base_lo + ((lane1 * st.d_lo) >> 5);
+    q_b = q_a + st.d_lo;
+    uint32_t t_hi_a = acc.t((uint32_t)g_a);
+    const uint32_t t_hi1_a = acc.t((uint32_t)(g_a + 1));
+    const uint32_t t_lo1_a = acc.t(q_a - 1u);
+    uint32_t t_lo_a = acc.t(q_a);
+    uint32_t t_hi_b = acc.t((uint32_t)g_b);
+    const uint32_t t_hi1_b = acc.t((uint32_t)(g_b + 1));
+    const uint32_t t_lo1_b = acc.t(q_b - 1u);
+    uint32_t t_lo_b = acc.t(q_b);
+    const bool good = (t_hi_a <= te) && (t_hi1_a > te) && (t_lo1_a <= tlo_a) && (t_lo_a > tlo_a) && ((int32_t)q_a <= g_a) &&
+                      (t_hi_b <= te_b) && (t_hi1_b > te_b) && (t_lo1_b <= tlo_b) && (t_lo_b > tlo_b) && ((int32_t)q_b <= g_b);
+    if (__all_sync(0xffffffffu, good)) {
+      st.base_hi += 2 * (int32_t)st.d_hi;
+      st.base_lo += 2u * st.d_lo;
+    } else {
+      // Repair in place (the usual miss: a sample exactly on a window edge shifts a few guesses by one): every lane
+      // walks both steps to their definitional edges — the newest sample is younger than both window ends and slot
+      // base_lo - 1 / the -1 sentinel bound the walks — and the pair goes on if the short form of lean_group holds
+      // for all 64 steps (non-empty windows, at most two samples of advance per step => every cursor start is
+      // <= lo + 1 <= top < m).  Nothing of the warp state has been touched yet, so "false" still means "one at a time".
+      while (acc.t((uint32_t)(g_a + 1)) <= te) ++g_a;
+      while (acc.t((uint32_t)g_a) > te) --g_a;
+      q_a = q_a > (uint32_t)(g_a + 1) ? (uint32_t)(g_a + 1) : q_a;
+      while (acc.t(q_a - 1u) > tlo_a) --q_a;
+      while (acc.t(q_a) <= tlo_a) ++q_a;
+      while (acc.t((uint32_t)(g_b + 1)) <= te_b) ++g_b;
+      while (acc.t((uint32_t)g_b) > te_b) --g_b;
+      q_b = q_b > (uint32_t)(g_b + 1) ? (uint32_t)(g_b + 1) : q_b;
+      while (acc.t(q_b - 1u) > tlo_b) --q_b;
+      while (acc.t(q_b) <= tlo_b) ++q_b;
+      uint32_t prev_a = __shfl_up_sync(0xffffffffu, q_a, 1);
+      uint32_t prev_b = __shfl_up_sync(0xffffffffu, q_b, 1);
+      const uint32_t last_a = __shfl_sync(0xffffffffu, q_a, 31);
+      if (lane == 0) {
+        prev_a = st.base_lo;
+        prev_b = last_a;
+      }
+      const bool fine = ((int32_t)q_a <= g_a) && ((int32_t)q_b <= g_b) && (q_a - prev_a <= 2u) && (q_b - prev_b <= 2u);
+      if (!__all_sync(0xffffffffu, fine)) return false;
+      t_hi_a = acc.t((uint32_t)g_a);
+      t_lo_a = acc.t(q_a);
+      t_hi_b = acc.t((uint32_t)g_b);
+      t_lo_b = acc.t(q_b);
+      const int32_t nhi = __shfl_sync(0xffffffffu, g_b, 31);
+      const uint32_t nlo = __shfl_sync(0xffffffffu, q_b, 31);
+      st.d_hi = (uint32_t)(nhi - st.base_hi + 1) >> 1;  // advance per group over the 64 steps
+      st.d_lo = (nlo - st.base_lo + 1u) >> 1;
+      st.base_hi = nhi;
+      st.base_lo = nlo;
+    }
+    if constexpr (GROUPED) { s_a = out_p[0]; s_b = out_p[32]; }  // the running partials are requested before the values
+    r_a = lean_value<FN, FLAGS>(a, acc, g_a, q_a, t_lo_a, t_hi_a, te, ok_a);
+    if constexpr (!GROUPED) out_p[0] = r_a;
+    r_b = lean_value<FN, FLAGS>(a, acc, g_b, q_b, t_lo_b, t_hi_b, te_b, ok_b);
+    if constexpr (!GROUPED) out_p[32] = r_b;
+  }
+  const uint32_t vw_a = __ballot_sync(0xffffffffu, ok_a), vw_b = __ballot_sync(0xffffffffu, ok_b);
   if constexpr (GROUPED) {
-    // the running partials of both steps are requested before the values are computed
-    const double s_a = out_p[0], s_b = out_p[32];
-    const double r_a = lean_value<FN, FLAGS>(a, acc, g_a, q_a, t_lo_a, t_hi_a, te, ok_a);
-    const double r_b = lean_value<FN, FLAGS>(a, acc, g_b, q_b, t_lo_b, t_hi_b, te_b, ok_b);
-    const uint32_t vw_a = __ballot_sync(0xffffffffu, ok_a), vw_b = __ballot_sync(0xffffffffu, ok_b);
     if (ok_a) out_p[0] = s_a + r_a;
     if (ok_b) out_p[32] = s_b + r_b;
     if ((vw_a & vw_b) == 0xffffffffu) {  // both words valid throughout: two per-warp counters instead of 64 counts
@@ -401,22 +531,22 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
         vw_p[lane + 32] = vw_p[lane + 32] + 1u;
       }
     }
-    return true;
-  }
-  const double r_a = lean_value<FN, FLAGS>(a, acc, g_a, q_a, t_lo_a, t_hi_a, te, ok_a);
-  out_p[0] = r_a;
-  const double r_b = lean_value<FN, FLAGS>(a, acc, g_b, q_b, t_lo_b, t_hi_b, te_b, ok_b);
-  out_p[32] = r_b;
-  const uint32_t vw_a = __ballot_sync(0xffffffffu, ok_a), vw_b = __ballot_sync(0xffffffffu, ok_b);
-  if (lane == 0) {
-    vw_p[0] = vw_a;
-    vw_p[1] = vw_b;
+  } else {
+    if (lane == 0) {
+      vw_p[0] = vw_a;
+      vw_p[1] = vw_b;
+    }
   }
   return true;
 }
 
-template <int FN, bool FLAGS, bool GROUPED = false>
+template <int FN, bool FLAGS, bool GROUPED = false, bool UNI = false>
 __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_lean_kernel(const RangeArgs a) {
+  static_assert(!UNI || kLeanUniform<FN, FLAGS>, "no uniform-cadence variant of this instantiation");
+  // functions with a uniform-cadence variant: the call launches both kernels, the probe's verdict keeps one
+  if constexpr (kLeanUniform<FN, FLAGS>) {
+    if ((a.status->uniform != 0u) != UNI) return;
+  }
   using LeanRing = LeanRingT<FLAGS>;
   constexpr int RING = kLeanRing;
   using TR = FnTraits<FN>;
@@ -424,13 +554,14 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // smem: [warps][RING] val f64 | [warps][2*RING] ts u32 | [kRcpTable] f64 | [warps][2][64] ts i64 |
   //       [warps][2][64] val f64 (staging of the block being fetched and the block being consumed) |
-  //       [warps][RING/32] reset / change bit words (FLAGS variant)
+  //       [warps][RING/32] reset / change bit words (FLAGS variant) | [warps] 32 B window-shape cache
   double* rval = reinterpret_cast<double*>(smem_raw) + warp * RING;
   uint32_t* rts = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kLeanWarps * RING * 8) + warp * (2 * RING);
   double* rcp_tab = reinterpret_cast<double*>(smem_raw + (size_t)kLeanWarps * RING * 16);
   // staging slots of this lane (shared-space byte addresses): [2 halves][64] per warp and column, 8 B elements
-  const uint32_t stage_t = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable) + (uint32_t)(warp * 128 + lane) * 8u;
-  const uint32_t stage_v = stage_t + (uint32_t)kLeanWarps * 128u * 8u;
+  const uint32_t stage_t = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable) + (uint32_t)(warp * (64 * kLeanDepth) + lane) * 8u;
+  const uint32_t stage_v = stage_t + (uint32_t)kLeanWarps * (64u * kLeanDepth) * 8u;
+  constexpr uint32_t kStageBytes = 512u * kLeanDepth;  // per warp and column
   for (int i = threadIdx.x; i < kRcpTable; i += blockDim.x) rcp_tab[i] = (i > 0) ? 1.0 / (double)i : 0.0;
   __syncthreads();
   LeanRing acc;
@@ -438,8 +569,10 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
   acc.val = rval;
   acc.rcp_tab = rcp_tab;
   acc.init_addresses();
-  acc.flags_sa = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable + kLeanWarps * 256) + (uint32_t)warp * (RING / 32) * 4u;
+  acc.flags_sa = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable + kLeanWarps * 128 * kLeanDepth) + (uint32_t)warp * (RING / 32) * 4u;
   acc.no_flags = true;
+  acc.shape_sa = acc.flags_sa - (uint32_t)warp * (RING / 32) * 4u + (uint32_t)kLeanWarps * (RING / 32) * 4u + (uint32_t)warp * 32u;
+  if (lane == 0) sts32(acc.shape_sa + 24u, 0xffffffffu);  // no shape cached yet (a window length never is 2^32 - 1)
   // GROUPED: per-warp "valid throughout" counters of the current group, one per 32-step word (behind everything else)
   uint32_t* const full_w = reinterpret_cast<uint32_t*>(smem_raw + lean_smem_bytes()) + warp * kLeanFullWords;
   if constexpr (GROUPED) {
@@ -461,9 +594,13 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
     const uint32_t cnt = rows > 0xfffffff0ull ? 0u : (uint32_t)rows;  // oversize series are not evaluated here
     const long long* pt0 = reinterpret_cast<const long long*>(a.ts + r0) + lane;
     const double* pv0 = a.val + r0 + lane;
-    if ((uint32_t)lane < cnt) { cp_async8(stage_t, pt0); cp_async8(stage_v, pv0); }
-    if ((uint32_t)lane + 32u < cnt) { cp_async8(stage_t + 256u, pt0 + 32); cp_async8(stage_v + 256u, pv0 + 32); }
-    cp_async_commit();
+#pragma unroll
+    for (int d = 0; d < kLeanDepth - 1; ++d) {  // blocks 0 .. depth-2, one commit group each (empty past the end)
+      const uint32_t o = 512u * d, r = 64u * d + (uint32_t)lane;
+      if (r < cnt) { cp_async8(stage_t + o, pt0 + 64 * d); cp_async8(stage_v + o, pv0 + 64 * d); }
+      if (r + 32u < cnt) { cp_async8(stage_t + o + 256u, pt0 + 64 * d + 32); cp_async8(stage_v + o + 256u, pv0 + 64 * d + 32); }
+      cp_async_commit();
+    }
   };
   // GROUPED: the warp walks whole groups, each group's member series in CSR order; groups are dealt out dynamically
   // (one atomic counter per launch) so that CTAs which start late — the all-reduce of the previous tile may hold a few
@@ -542,6 +679,7 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
       double* const out_p0 = out_p;
       LeanState st;
       st.j_cnt = 0; st.base_lo = 0; st.base_hi = -1; st.d_lo = 0; st.d_hi = 32; st.phase = 0; st.last_flag = 0;
+      st.reg_from = 0;
       uint32_t te = te_lane0;                                      // window end of step k_next + lane
       uint32_t te31 = (uint32_t)a.range + 31u * (uint32_t)a.interval;  // ... of step k_next + 31
       __syncwarp();
@@ -551,46 +689,63 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
       // in flight into the other half of the staging area (cp.async, one commit group per block)
       const long long* p_t = reinterpret_cast<const long long*>(ts_s) + lane;
       const double* p_v = val_s + lane;
-      uint32_t half = 0;  // staging half (byte offset 0 or 512) of the block being consumed
+      uint32_t half = 0;                              // staging slot (byte offset) of the block being consumed
+      uint32_t ahead = 512u * (kLeanDepth - 1);       // ... of the block put in flight next
       while (st.j_cnt < n) {
         const uint32_t j0 = st.j_cnt;  // multiple of 64
         const uint32_t left = n - j0;
         const bool in0 = (uint32_t)lane < left, in1 = (uint32_t)lane + 32u < left;
         {
-          const uint32_t other = half ^ 512u;
-          if ((uint32_t)lane + 64u < left) { cp_async8(stage_t + other, p_t + 64); cp_async8(stage_v + other, p_v + 64); }
-          if ((uint32_t)lane + 96u < left) { cp_async8(stage_t + other + 256u, p_t + 96); cp_async8(stage_v + other + 256u, p_v + 96); }
+          constexpr uint32_t kA = 64u * (kLeanDepth - 1);  // rows ahead
+          if ((uint32_t)lane + kA < left) { cp_async8(stage_t + ahead, p_t + kA); cp_async8(stage_v + ahead, p_v + kA); }
+          if ((uint32_t)lane + kA + 32u < left) { cp_async8(stage_t + ahead + 256u, p_t + kA + 32); cp_async8(stage_v + ahead + 256u, p_v + kA + 32); }
           cp_async_commit();
           p_t += 64;
           p_v += 64;
+          ahead = ahead + 512u == kStageBytes ? 0u : ahead + 512u;
         }
-        cp_async_wait<1>();  // everything but the newest group: the block to consume has landed
+        cp_async_wait<kLeanDepth - 1>();  // everything but the newest depth-1 groups: the block to consume has landed
         const long long c_t0 = lds_s64(stage_t + half), c_t1 = lds_s64(stage_t + half + 256u);
         const double c_v0 = LeanRing::lds64(stage_v + half), c_v1 = LeanRing::lds64(stage_v + half + 256u);
-        half ^= 512u;
+        half = half + 512u == kStageBytes ? 0u : half + 512u;
         // SeriesNormalize (offset bias) + 32-bit time domain, append to the ring: the block occupies slots
         // (j0 mod RING) + [0, 64), which never wrap, and their mirrors RING further
         const uint32_t slot = (j0 & (uint32_t)(RING - 1)) + (uint32_t)lane;
         const uint32_t pt = acc.ts_sa + slot * 4u;  // shared-space addresses of the lane's first row
         const uint32_t pv = acc.val_sa + slot * 8u;
+        uint32_t r0, r1;
         {
           const long long d = c_t0 - tb_off;
           const int32_t dh = (int32_t)(d >> 32);
           const uint32_t dl = (uint32_t)d;
           const uint32_t in = dl < a.rel_max ? dl : a.rel_max;
-          const uint32_t r = dh == 0 ? in : (dh < 0 ? 0u : a.rel_max);
-          if (in0) { sts32(pt, r); sts32(pt + RING * 4u, r); sts64(pv, c_v0); }
+          r0 = dh == 0 ? in : (dh < 0 ? 0u : a.rel_max);
+          if (in0) { sts32(pt, r0); sts32(pt + RING * 4u, r0); sts64(pv, c_v0); }
         }
         {
           const long long d = c_t1 - tb_off;
           const int32_t dh = (int32_t)(d >> 32);
           const uint32_t dl = (uint32_t)d;
           const uint32_t in = dl < a.rel_max ? dl : a.rel_max;
-          const uint32_t r = dh == 0 ? in : (dh < 0 ? 0u : a.rel_max);
-          if (in1) { sts32(pt + 128u, r); sts32(pt + 128u + RING * 4u, r); sts64(pv + 256u, c_v1); }
+          r1 = dh == 0 ? in : (dh < 0 ? 0u : a.rel_max);
+          if (in1) { sts32(pt + 128u, r1); sts32(pt + 128u + RING * 4u, r1); sts64(pv + 256u, c_v1); }
         }
         __syncwarp();
         bool bad = (a.filter_nan != 0) & ((in0 & isnan(c_v0)) | (in1 & isnan(c_v1)));
+        // uniform cadence: is every new sample exactly one eval interval after its predecessor (the mirror of slot - 1
+        // and slot + 31; the first sample of a series has none)?  A break behind a sample clamped to 0 (history before
+        // start - range) only restarts the run; any other break gives the series up for this path (reg_from = ~0), so
+        // jittered series pay for one block's check only.
+        bool odd = false, hard = false;
+        if constexpr (UNI) {
+          if (st.reg_from != 0xffffffffu) {
+            const uint32_t pr0 = LeanRing::lds32(pt + RING * 4u - 4u), pr1 = LeanRing::lds32(pt + 124u);
+            const bool o0 = in0 & ((j0 | (uint32_t)lane) != 0u) & (r0 - pr0 != (uint32_t)a.interval);
+            const bool o1 = in1 & (r1 - pr1 != (uint32_t)a.interval);
+            odd = o0 | o1;
+            hard = (o0 & (pr0 != 0u)) | (o1 & (pr1 != 0u));
+          }
+        }
         if constexpr (FLAGS) {
           // reset / change bit of every new sample against its predecessor (slot -1 of a series holds -inf, so
           // its first sample is never a reset; for changes() it is masked explicitly): the block is 64-aligned,
@@ -613,13 +768,17 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
           const double p1 = LeanRing::lds64(pv + 248u);
           bad = bad | (in0 & (c_v0 < p0)) | (in1 & (c_v1 < p1));
         }
-        if (__any_sync(0xffffffffu, bad)) { defer = 4; break; }
+        if (__any_sync(0xffffffffu, bad | odd)) {
+          if (__any_sync(0xffffffffu, bad)) { defer = 4; break; }
+          // the run of equally spaced samples restarts at the newest one, or the series is not one of those
+          st.reg_from = __any_sync(0xffffffffu, hard) ? 0xffffffffu : j0 + (left < 64u ? left : 64u) - 1u;
+        }
         if constexpr (FLAGS) __syncwarp();  // the bit words are read by every lane below
         st.j_cnt = j0 + (left < 64u ? left : 64u);
         const uint32_t t_new = acc.tm(st.j_cnt - 1u);
         // every group whose last window end is older than the newest sample is final
         while (te31 < t_new) {
-          if (B2P_LEAN_PAIR && te31 + step32 < t_new && lean_pair<FN, FLAGS, GROUPED>(a, st, acc, te, step32, out_p, vw_p, lane, full_p)) {
+          if (B2P_LEAN_PAIR && te31 + step32 < t_new && lean_pair<FN, FLAGS, GROUPED, UNI>(a, st, acc, te, step32, out_p, vw_p, lane, full_p)) {
             te += 2u * step32;
             te31 += 2u * step32;
             out_p += 64;
@@ -738,5 +897,35 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
 }
 
 __host__ __device__ constexpr size_t lean_grouped_smem_bytes() { return lean_smem_bytes() + (size_t)kLeanWarps * kLeanFullWords * 4; }
+
+// Which first-tier variant a call runs (rate / increase / delta, plain): one CTA looks at up to 1024 series spread over
+// the call and counts those whose first (up to) 32 timestamp deltas all equal the eval interval; when at least half of
+// them do, Status::uniform is set and the uniform-cadence kernel runs, else the general one.  Only a performance choice:
+// both kernels check what they rely on sample by sample and produce the same bits.
+constexpr int kProbeThreads = 1024;
+__global__ void __launch_bounds__(kProbeThreads) cadence_probe_kernel(const RangeArgs a) {
+  __shared__ uint32_t cnt[2];
+  if (threadIdx.x < 2) cnt[threadIdx.x] = 0u;
+  __syncthreads();
+  const uint32_t k = a.n_series < (uint32_t)kProbeThreads ? a.n_series : (uint32_t)kProbeThreads;
+  if (threadIdx.x < k) {
+    const uint32_t s = (uint32_t)(((uint64_t)threadIdx.x * a.n_series) / k);
+    const uint64_t r0 = a.offsets[s], r1 = a.offsets[s + 1];
+    if (r1 - r0 >= 2ull) {
+      const uint64_t m = r1 - r0 < 33ull ? r1 - r0 : 33ull;
+      bool regular = true;
+      int64_t prev = a.ts[r0];
+      for (uint64_t i = 1; i < m; ++i) {
+        const int64_t t = a.ts[r0 + i];
+        regular = regular && (t - prev == a.interval);
+        prev = t;
+      }
+      atomicAdd(&cnt[0], 1u);
+      if (regular) atomicAdd(&cnt[1], 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) a.status->uniform = (cnt[0] > 0u && cnt[1] * 2u >= cnt[0]) ? 1u : 0u;
+}
 
 }  // namespace b2p

@@ -34,6 +34,7 @@ struct Status {
   uint32_t w_count;         // series the first tier handed to the warp-per-series kernel
   uint32_t b_count;         // series the warp-per-series kernel handed to its long-window (big ring) instantiation
   uint32_t g_next;          // fused by-label partials: next group (relative to g_lo) a first-tier warp takes
+  uint32_t uniform;         // cadence_probe_kernel's verdict: != 0 => the uniform-cadence variant of the first tier runs
   unsigned long long arena_used;    // (unused since the arena is split into per-warp regions)
   unsigned long long arena_needed;  // arena rows that make a region large enough for the longest deferred series
 };

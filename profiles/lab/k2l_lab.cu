@@ -11,6 +11,9 @@
 #include <cstring>
 
 #include "b2p_kernel_lean.cuh"
+#ifdef LAB_K2U
+#include "k2u_experiment.cuh"
+#endif
 
 using namespace b2p;
 
@@ -83,7 +86,11 @@ int main(int argc, char** argv) {
   a.b_list = nullptr;
 #endif
 
-  auto kern = range_lean_kernel<LAB_FN, LAB_FLAGS>;
+#ifndef LAB_UNI
+#define LAB_UNI false
+#endif
+  auto kern = range_lean_kernel<LAB_FN, LAB_FLAGS, false, LAB_UNI>;
+  if (LAB_UNI) CK(cudaMemset(&status->uniform, 1, 4));
 #ifdef LAB_REF
   constexpr int kLeanWarps = kWarpsPerCta;
   constexpr size_t smem = (size_t)kWarpsPerCta * kLeanRing * 16 + kRcpTable * 8 + (size_t)kWarpsPerCta * 2 * 64 * 16 +
@@ -106,10 +113,26 @@ int main(int argc, char** argv) {
     if (blocks > 148ull * 16) blocks = 148ull * 16;
     series_offsets_kernel<<<(unsigned)blocks, 256, 0, st>>>(sid, n_rows, S, 0u, offsets, status);
   };
+#ifdef LAB_K2U
+  auto ukern = range_uniform_kernel<LAB_FN>;
+  int unb = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&unb, ukern, kUniWarps * 32, 0));
+  CK(cudaFuncGetAttributes(&fa, ukern));
+  nb = unb;
+  CK(cudaMemset(&status->uniform, 1, 4));
+  const unsigned uneed = (S + kUniWarps - 1) / kUniWarps;
+  const unsigned ucap = 148u * (unsigned)(getenv("LAB_K2U_CTAS_PER_SM") ? atoi(getenv("LAB_K2U_CTAS_PER_SM")) : unb);
+  const unsigned ugrid = uneed < ucap ? uneed : ucap;
+  auto run_k2l = [&]() {
+    cudaMemsetAsync(&status->w_count, 0, 4, st);
+    ukern<<<ugrid, kUniWarps * 32, 0, st>>>(a);
+  };
+#else
   auto run_k2l = [&]() {
     cudaMemsetAsync(&status->w_count, 0, 4, st);
     kern<<<grid, kLeanWarps * 32, smem, st>>>(a);
   };
+#endif
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   auto timeit = [&](auto f) {

@@ -55,8 +55,12 @@ for rep in args:
             full = r[hdr.index("Kernel Name")]
             plain = full.replace("(bool)", "").replace("(int)", "").replace("b2p::", "")
             key = plain.split("(")[0].split("<")[0].replace("void ", "").strip()
-            if key == "range_lean_kernel" and plain.split(">")[0].rstrip().endswith("1"):
-                key = "range_lean_kernel_grouped"  # template <FN, FLAGS, GROUPED>
+            if key == "range_lean_kernel":  # template <FN, FLAGS, GROUPED, UNI>
+                targs = [x.strip() for x in plain.split("<", 1)[1].split(">")[0].split(",")]
+                if len(targs) > 2 and targs[2] == "1":
+                    key += "_grouped"
+                if len(targs) > 3 and targs[3] == "1":
+                    key += "_uniform"
             if key not in traffic:
                 b = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
                 traffic[key] = {"dram_bytes_per_launch": b, "dram_bytes_per_sample": b / samples,

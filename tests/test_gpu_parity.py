@@ -446,6 +446,88 @@ def test_lean_tier_keeps_regular_series_and_hands_off_the_rest(ctx, ctx_no_lean)
     assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size), "lean tier NaN hand-off")
 
 
+def make_uniform_cadence(seed, n_series, scrape=15_000, t0=1_700_000_000_000):
+    """Ragged series sampled exactly every `scrape` ms (the layout of aligned scrapes): different lengths and start
+    phases; every 7th series carries a defect: a NaN sample or a counter reset (the series has to leave the first
+    tier), one late scrape or a missing scrape (the run of equally spaced samples restarts behind it).
+    -> ts, val, offsets, defect kind per series (-1 none, 0 NaN, 1 reset, 2 late, 3 gap)"""
+    rng = np.random.default_rng(seed)
+    ts_l, val_l, offs, defect = [], [], [0], []
+    for s in range(n_series):
+        n = int(rng.integers(1, 700)) if s % 5 else int(rng.integers(1, 30))
+        first = t0 + int(rng.integers(-40, 200)) * scrape + (int(rng.integers(0, scrape)) if s % 3 == 0 else 0)
+        t = first + np.arange(n, dtype=np.int64) * scrape
+        v = np.cumsum(rng.random(n) * 10) + (0.0 if s % 4 else 1e6)
+        kind = s % 7 if n > 8 else 1
+        if kind == 0:
+            j = int(rng.integers(1, n - 1))
+            which = (s // 7) % 4
+            if which == 0:
+                v[j] = np.nan
+            elif which == 1:
+                v[j:] -= v[j] * 0.9
+            elif which == 2:
+                t[j] += 1
+            else:
+                t[j:] += scrape
+        defect.append((s // 7) % 4 if kind == 0 else -1)
+        ts_l.append(t)
+        val_l.append(v.astype(np.float64))
+        offs.append(offs[-1] + n)
+    return np.concatenate(ts_l), np.concatenate(val_l), np.array(offs, np.uint64), np.array(defect)
+
+
+@pytest.mark.parametrize("fn", ["rate", "increase", "delta"])
+def test_uniform_cadence_tier_matches_oracle_and_the_general_tiers(ctx, ctx_no_lean, fn):
+    """The uniform-cadence variant of K2L (series sampled exactly at the eval interval): window edges without
+    verification reads, one extrapolation factor per window shape.  Bit-identical to the general kernels and equal to
+    the oracle on ragged regular series — windows cut by either end of a series, history before the query, queries
+    ending after the data, the offset modifier, range == interval, timestamps off the grid in the middle of a series
+    — and the series with a NaN sample or a counter reset leave the tier as they do on the general variant."""
+    import os
+    from greptimedb_b200 import Context, make_params
+    T0, SC = 1_700_000_000_000, 15_000
+    ts, val, offsets, defect = make_uniform_cadence(77, 420)
+    S = offsets.size - 1
+    os.environ["B2P_LEAN_ADAPTIVE"] = "0"
+    os.environ["B2P_UNIFORM"] = "1"   # (the probe would pick it as well: most series are regular)
+    try:
+        forced = Context(0)
+    finally:
+        del os.environ["B2P_LEAN_ADAPTIVE"], os.environ["B2P_UNIFORM"]
+    try:
+        for start, end, rng_ms, offset in (
+                (T0, T0 + 999 * SC, 300_000, 0),                    # BASELINE geometry
+                (T0 + 7, T0 + 400 * SC + 7, 300_000, 0),             # steps off the scrape grid
+                (T0 - 100 * SC, T0 + 900 * SC, 15_000, 0),           # range == interval: one-sample windows are null
+                (T0 + 300 * SC + 14_999, T0 + 1200 * SC, 77_777, 0),  # history before the query, steps past the data
+                (T0 + 500 * SC, T0 + 520 * SC, 1_000_000, 0),        # late start: the cursor-start quirk on short series
+                (T0 + 50 * SC, T0 + 800 * SC, 600_000, 45_000)):     # offset modifier
+            p = make_params(fn, start, end, SC, rng_ms, offset=offset)
+            out, valid, ets = forced.range_eval(p, ts, val, offsets=offsets)
+            handed = forced.last_warp_tier_series()
+            out2, valid2, _ = ctx_no_lean.range_eval(p, ts, val, offsets=offsets)
+            tag = (fn, start - T0, rng_ms, offset)
+            vb, vb2 = orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(valid2, ets.size)
+            assert (vb == vb2).all(), tag
+            assert (out.view(np.uint64)[vb] == out2.view(np.uint64)[vb]).all(), tag
+            op = orc.make_params(fn, start, end, SC, rng_ms, offset=offset)
+            e_out, e_valid = orc.range_query(op, ts, val, None, offsets, mode="faithful", threads=4)
+            assert_close(out, e_out, vb, orc.valid_to_bool(e_valid, ets.size), f"uniform tier {tag}")
+            # NaN samples and (for counters) resets send a series on; the other series stay unless the quirk applies
+            must = int((defect == 0).sum()) + (0 if fn == "delta" else int((defect == 1).sum()))
+            if end >= T0 + 900 * SC and start <= T0:   # (a reset behind the last window of a short query is never reached)
+                assert handed >= must, (tag, handed, must)
+            assert handed <= S // 2, (tag, handed)
+        # the device probe picks the tier by itself: same bits on regular data, and jittered data takes the other kernel
+        p = make_params(fn, T0, T0 + 999 * SC, SC, 300_000)
+        out_a, valid_a, _ = ctx.range_eval(p, ts, val, offsets=offsets)
+        out_f, valid_f, _ = forced.range_eval(p, ts, val, offsets=offsets)
+        assert (valid_a == valid_f).all() and (out_a.view(np.uint64) == out_f.view(np.uint64)).all()
+    finally:
+        forced.close()
+
+
 def test_lean_tier_backs_off_after_a_call_it_mostly_declined(ctx_no_lean):
     """Adaptive tiering (default on): a call in which K2L hands more than half of the series to K2 makes the following
     calls skip K2L; results are the same either way."""
