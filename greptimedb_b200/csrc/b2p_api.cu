@@ -161,7 +161,10 @@ struct b2p_ctx {
   Nccl::comm_t comm = nullptr;
   int comm_ranks = 1, comm_rank = 0;
   long long comm_headstart_cycles = 60000;  // ~30 us at 1.965 GHz (B2P_COMM_HEADSTART_US overrides)
-  int comm_reserve_sms = 8;                 // SMs the fused tier leaves to the tile all-reduce (B2P_COMM_RESERVE_SMS)
+  // SMs the fused tier leaves to the tile all-reduce (B2P_COMM_RESERVE_SMS).  Off: measured at 2 GPUs, 0 / 8 / 16 SMs
+  // left free give 12.0 / 12.3 / 14.2 ms per step — the all-reduce of a tile still does not run beside the next tile's
+  // kernel, the step only loses the SMs
+  int comm_reserve_sms = 0;
   int comm_reserve_now = 0;                 // ... in effect for the launch being issued
   cudaStream_t s_comm = nullptr;
   cudaEvent_t ev_comm_in = nullptr, ev_comm_done = nullptr, ev_comm_go = nullptr;

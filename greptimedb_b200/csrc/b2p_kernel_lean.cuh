@@ -899,7 +899,7 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
 __host__ __device__ constexpr size_t lean_grouped_smem_bytes() { return lean_smem_bytes() + (size_t)kLeanWarps * kLeanFullWords * 4; }
 
 // Which first-tier variant a call runs (rate / increase / delta, plain): one CTA looks at up to 1024 series spread over
-// the call and counts those whose first (up to) 32 timestamp deltas all equal the eval interval; when at least half of
+// the call and counts those whose first (up to) 8 timestamp deltas all equal the eval interval; when at least half of
 // them do, Status::uniform is set and the uniform-cadence kernel runs, else the general one.  Only a performance choice:
 // both kernels check what they rely on sample by sample and produce the same bits.
 constexpr int kProbeThreads = 1024;
@@ -912,14 +912,13 @@ __global__ void __launch_bounds__(kProbeThreads) cadence_probe_kernel(const Rang
     const uint32_t s = (uint32_t)(((uint64_t)threadIdx.x * a.n_series) / k);
     const uint64_t r0 = a.offsets[s], r1 = a.offsets[s + 1];
     if (r1 - r0 >= 2ull) {
-      const uint64_t m = r1 - r0 < 33ull ? r1 - r0 : 33ull;
+      const uint64_t m = r1 - r0 < 9ull ? r1 - r0 : 9ull;
+      int64_t t[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) t[i] = (uint64_t)i < m ? a.ts[r0 + i] : 0;  // (independent loads, one round trip)
       bool regular = true;
-      int64_t prev = a.ts[r0];
-      for (uint64_t i = 1; i < m; ++i) {
-        const int64_t t = a.ts[r0 + i];
-        regular = regular && (t - prev == a.interval);
-        prev = t;
-      }
+#pragma unroll
+      for (int i = 1; i < 9; ++i) regular = regular && ((uint64_t)i >= m || t[i] - t[i - 1] == a.interval);
       atomicAdd(&cnt[0], 1u);
       if (regular) atomicAdd(&cnt[1], 1u);
     }
