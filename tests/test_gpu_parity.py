@@ -788,9 +788,9 @@ def test_device_api_sum_by_partials_and_finalize(ctx):
     assert rel[e_cnt > 0].max() <= 1e-9
 
 
-def _sum_by_case(S, N, G, resets, nan_every, seed, gid_mode="hash"):
+def _sum_by_case(S, N, G, resets, nan_every, seed, gid_mode="hash", jitter=1000):
     T0 = 1_700_000_000_000
-    ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, 1000, resets, seed)
+    ts, val, sid = orc.synth_fill(0, S, N, T0, 15_000, jitter, resets, seed)
     if nan_every:
         val[nan_every // 2::nan_every] = np.nan
     offsets = np.arange(S + 1, dtype=np.uint64) * N
@@ -802,9 +802,11 @@ def _sum_by_case(S, N, G, resets, nan_every, seed, gid_mode="hash"):
     return T0, ts, val, sid, offsets, gid
 
 
-@pytest.mark.parametrize("fn,resets,nan_every", [("rate", 0, 0), ("rate", 1, 0), ("rate", 0, 9973), ("increase", 1, 7919),
-                                                  ("delta", 0, 0), ("delta", 1, 4099)])
-def test_fused_sum_by_matches_oracle_and_two_pass(ctx, ctx_lean_flags, fn, resets, nan_every):
+@pytest.mark.parametrize("fn,resets,nan_every,jitter", [("rate", 0, 0, 1000), ("rate", 1, 0, 1000), ("rate", 0, 9973, 1000),
+                                                         ("increase", 1, 7919, 1000), ("delta", 0, 0, 1000), ("delta", 1, 4099, 1000),
+                                                         # scrapes on the schedule: the uniform-cadence variant of the fused tier
+                                                         ("rate", 0, 0, 0), ("rate", 0, 9973, 0), ("increase", 1, 7919, 0), ("delta", 1, 4099, 0)])
+def test_fused_sum_by_matches_oracle_and_two_pass(ctx, ctx_lean_flags, fn, resets, nan_every, jitter):
     """sum by (..)(rate(..)) without the [S x T] intermediate (b2p_range_group_sum_indexed_dev): the first tier adds
     group by group, series it hands on (counter resets on the plain variant, NaN samples) are added by the later tiers
     from the step where the first tier stopped.  Checked against the oracle's rate + group aggregate and against the
@@ -813,7 +815,7 @@ def test_fused_sum_by_matches_oracle_and_two_pass(ctx, ctx_lean_flags, fn, reset
     from greptimedb_b200 import make_params
     dev = torch.device("cuda:0")
     S, N, G = 1500, 700, 97
-    T0, ts, val, sid, offsets, gid = _sum_by_case(S, N, G, resets, nan_every, 11)
+    T0, ts, val, sid, offsets, gid = _sum_by_case(S, N, G, resets, nan_every, 11, jitter=jitter)
     p = make_params(fn, T0, T0 + (N - 1) * 15_000, 15_000, 300_000)
     T = N
     op = orc.make_params(fn, T0, T0 + (N - 1) * 15_000, 15_000, 300_000)
