@@ -345,7 +345,7 @@ static int cadence_verdict(b2p_ctx* c, const RangeArgs& a) {
 
 template <int FN, bool FLAGS, bool UNI>
 int launch_lean_variant(b2p_ctx* c, const RangeArgs& a) {
-  constexpr size_t smem = lean_smem_bytes();
+  constexpr size_t smem = lean_smem_bytes(UNI);
   auto kern = range_lean_kernel<FN, FLAGS, false, UNI>;
   int& cached = c->lean_blocks_per_sm[FN][FLAGS ? 1 : 0][UNI ? 1 : 0];
   if (cached == 0) {
@@ -395,7 +395,7 @@ int launch_lean_if_supported(b2p_ctx* c, const RangeArgs& a, bool with_flags) {
 // gsum / gcnt (range_lean_kernel<FN, FLAGS, GROUPED = true>).
 template <int FN, bool FLAGS, bool UNI>
 int launch_lean_grouped_variant(b2p_ctx* c, const RangeArgs& a) {
-  constexpr size_t smem = lean_grouped_smem_bytes();
+  constexpr size_t smem = lean_grouped_smem_bytes(UNI);
   auto kern = range_lean_kernel<FN, FLAGS, true, UNI>;
   static int cached_nb[16] = {};  // per device
   int& cached = cached_nb[c->device & 15];

@@ -55,15 +55,20 @@ constexpr int kLeanWarps = B2P_LEAN_WARPS;
 #define B2P_LEAN_DEPTH 2
 #endif
 constexpr int kLeanDepth = B2P_LEAN_DEPTH;
+// ... of the uniform-cadence kernel: with its steady form it is no longer issue bound and a third block in flight pays
+// (1.25 M series: 6.03 -> 5.80 ms; the general kernel: 7.62 -> 7.69)
+#ifndef B2P_LEAN_DEPTH_UNI
+#define B2P_LEAN_DEPTH_UNI 3
+#endif
+constexpr int kLeanDepthUni = B2P_LEAN_DEPTH_UNI;
 // dynamic shared memory of one CTA: value ring + mirrored timestamp ring + reciprocal table + staging (two 64-row
 // blocks per warp and column) + bit words + per-warp window-shape cache of the uniform-cadence path (32 B)
 // GROUPED (fused by-label partials): per-warp counters "members of the current group whose 32-step word k/32 was valid
 // throughout" — the by far most common word; they are added to the count row when the warp leaves the group, so the
 // hot path updates the per-step counts in global memory only for the few partially valid words
 constexpr int kLeanFullWords = 256;  // => T <= 8192 eval steps on the fused path (host gate)
-__host__ __device__ constexpr size_t lean_grouped_smem_bytes();
-__host__ __device__ constexpr size_t lean_smem_bytes() {
-  return (size_t)kLeanWarps * kLeanRing * 16 + kRcpTable * 8 + (size_t)kLeanWarps * kLeanDepth * 64 * 16 +
+__host__ __device__ constexpr size_t lean_smem_bytes(bool uni = false) {
+  return (size_t)kLeanWarps * kLeanRing * 16 + kRcpTable * 8 + (size_t)kLeanWarps * (uni ? kLeanDepthUni : kLeanDepth) * 64 * 16 +
          (size_t)kLeanWarps * (kLeanRing / 32) * 4 + (size_t)kLeanWarps * 32;
 }
 
@@ -318,6 +323,9 @@ __device__ __forceinline__ int lean_group(const RangeArgs& a, LeanState& st, Lea
 #ifndef B2P_LEAN_UNIFORM
 #define B2P_LEAN_UNIFORM 1
 #endif
+#ifndef B2P_LEAN_STEADY
+#define B2P_LEAN_STEADY 1
+#endif
 
 // The uniform-cadence path is compiled into the plain variants of the extrapolated functions (rate / increase / delta):
 // there the per-step arithmetic it removes dominates.  (With the reset bit words the correction scan dominates, and the
@@ -369,7 +377,7 @@ __device__ __forceinline__ double lean_value_shape(const RangeArgs& a, const Lea
 
 // Two consecutive groups (64 steps) in one go, steady state only: before the end of the stream, previous step
 // non-empty, at most one sample of advance per step (so no cursor start can reach m, see lean_group), and every
-// one of the 64 proportional guesses verified by one vote.  Returns false without side effects when any of that
+// one of the 64 proportional guesses verified by one vote.  Returns 0 without side effects when any of that
 // does not hold; the caller then takes the groups one at a time.
 //
 // Uniform cadence (B2P_LEAN_UNIFORM): when every sample from the one before the previous step's window up to the one
@@ -379,13 +387,20 @@ __device__ __forceinline__ double lean_value_shape(const RangeArgs& a, const Lea
 // The edges of all 64 windows follow from the previous step's without a single verification read, all windows have
 // the previous one's shape, and the cursor start of calculate_range is lo - 1 + 1 <= hi < m.  This is the layout of
 // aligned scrapes (Prometheus aligns scrape timestamps to the schedule; the BASELINE generator without jitter).
-template <int FN, bool FLAGS, bool GROUPED = false, bool UNI = false>
-__device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, LeanRingT<FLAGS>& acc, uint32_t te,
-                                          uint32_t step32, double* out_p, uint32_t* vw_p, int lane,
-                                          uint32_t* full_p = nullptr) {
+//
+// STEADY (uniform-cadence kernel): the block appended last is a full one without a break in the cadence and the block
+// before it was followed by exactly one uniform pair.  Then everything the gates and the shape look-up would compute
+// is what it was one block ago moved on by 64 samples / 64 steps (te31 + step32 < t_new, the run still covers the
+// windows, base_hi + 65 <= top, the same shape in the warp's cache slot): the pair is evaluated without any of it.
+// Returns 0 (nothing done), 1 (pair evaluated on verified guesses) or 2 (uniform pair).
+template <int FN, bool FLAGS, bool GROUPED = false, bool UNI = false, bool STEADY = false>
+__device__ __forceinline__ int lean_pair(const RangeArgs& a, LeanState& st, LeanRingT<FLAGS>& acc, uint32_t te,
+                                         uint32_t step32, double* out_p, uint32_t* vw_p, int lane,
+                                         uint32_t* full_p = nullptr) {
   using TR = FnTraits<FN>;
+  static_assert(!STEADY || (UNI && TR::kExtrapolated), "the steady form belongs to the uniform-cadence kernel");
   const int32_t top = (int32_t)st.j_cnt - 1;
-  if (st.phase != 1u) return false;
+  if (!STEADY && st.phase != 1u) return 0;
   const uint32_t rng = (uint32_t)a.range;
   const uint32_t lane1 = (uint32_t)lane + 1u;
   const uint32_t te_b = te + step32;
@@ -397,16 +412,22 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
   [[maybe_unused]] double s_a = 0.0, s_b = 0.0;
   // (reg_from < base_lo: the sample before the previous window is part of the run; base_hi + 65 <= top: so is the one
   // after the last window, and all of them have been appended)
-  const bool uniform = UNI && st.reg_from < st.base_lo && st.base_hi + 65 <= top;
+  const bool uniform = STEADY || (UNI && st.reg_from < st.base_lo && st.base_hi + 65 <= top);
   if (uniform) {
+    LeanShape sh;
+    sh.far = false;
+    sh.factor = 0.0;
+    if constexpr (STEADY) {
+      uint32_t k3;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(sh.to_end), "=r"(sh.to_start), "=r"(sh.len), "=r"(k3) : "r"(acc.shape_sa + 16u) : "memory");
+      sh.factor = LeanRingT<FLAGS>::lds64(acc.shape_sa);
+      sh.far = k3 != 0u;
+    } else {
     const uint32_t te_prev = te - lane1 * (uint32_t)a.interval;  // window end of the previous step
     const uint32_t t_hi_p = acc.tm((uint32_t)st.base_hi), t_lo_p = acc.tm(st.base_lo);
-    LeanShape sh;
     sh.to_end = te_prev - t_hi_p;
     sh.to_start = t_lo_p - (te_prev - rng);
     sh.len = (uint32_t)st.base_hi - st.base_lo + 1u;
-    sh.far = false;
-    sh.factor = 0.0;
     if constexpr (TR::kExtrapolated) {
       // factor of this shape: per-warp cache of the last shape (a series keeps one shape over its run)
       uint32_t k0, k1, k2, k3;
@@ -433,6 +454,7 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
         __syncwarp();
       }
     }
+    }
     g_a = st.base_hi + (int32_t)lane1;
     g_b = g_a + 32;
     q_a = st.base_lo + lane1;
@@ -448,7 +470,7 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
     if constexpr (!GROUPED) out_p[32] = r_b;
   } else {
     // uniform gates; the last two keep every read below the newest sample (slot top), i.e. on written slots
-    if (st.d_lo > 32u || st.base_hi + 2 * (int32_t)st.d_hi >= top || st.base_lo + 2u * st.d_lo > (uint32_t)top) return false;
+    if (st.d_lo > 32u || st.base_hi + 2 * (int32_t)st.d_hi >= top || st.base_lo + 2u * st.d_lo > (uint32_t)top) return 0;
     const uint32_t tlo_a = te - rng, tlo_b = te_b - rng;
     acc.set_window((int32_t)st.base_lo - 1);
     g_a = st.base_hi + (int32_t)((lane1 * st.d_hi) >> 5);
@@ -492,7 +514,7 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
         prev_b = last_a;
       }
       const bool fine = ((int32_t)q_a <= g_a) && ((int32_t)q_b <= g_b) && (q_a - prev_a <= 2u) && (q_b - prev_b <= 2u);
-      if (!__all_sync(0xffffffffu, fine)) return false;
+      if (!__all_sync(0xffffffffu, fine)) return 0;
       t_hi_a = acc.t((uint32_t)g_a);
       t_lo_a = acc.t(q_a);
       t_hi_b = acc.t((uint32_t)g_b);
@@ -510,7 +532,14 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
     r_b = lean_value<FN, FLAGS>(a, acc, g_b, q_b, t_lo_b, t_hi_b, te_b, ok_b);
     if constexpr (!GROUPED) out_p[32] = r_b;
   }
-  const uint32_t vw_a = __ballot_sync(0xffffffffu, ok_a), vw_b = __ballot_sync(0xffffffffu, ok_b);
+  uint32_t vw_a, vw_b;
+  if (TR::kExtrapolated && uniform) {  // one shape: every step of the pair is valid, or none is
+    vw_a = ok_a ? 0xffffffffu : 0u;
+    vw_b = vw_a;
+  } else {
+    vw_a = __ballot_sync(0xffffffffu, ok_a);
+    vw_b = __ballot_sync(0xffffffffu, ok_b);
+  }
   if constexpr (GROUPED) {
     if (ok_a) out_p[0] = s_a + r_a;
     if (ok_b) out_p[32] = s_b + r_b;
@@ -537,7 +566,7 @@ __device__ __forceinline__ bool lean_pair(const RangeArgs& a, LeanState& st, Lea
       vw_p[1] = vw_b;
     }
   }
-  return true;
+  return uniform ? 2 : 1;
 }
 
 template <int FN, bool FLAGS, bool GROUPED = false, bool UNI = false>
@@ -559,9 +588,10 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
   uint32_t* rts = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kLeanWarps * RING * 8) + warp * (2 * RING);
   double* rcp_tab = reinterpret_cast<double*>(smem_raw + (size_t)kLeanWarps * RING * 16);
   // staging slots of this lane (shared-space byte addresses): [2 halves][64] per warp and column, 8 B elements
-  const uint32_t stage_t = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable) + (uint32_t)(warp * (64 * kLeanDepth) + lane) * 8u;
-  const uint32_t stage_v = stage_t + (uint32_t)kLeanWarps * (64u * kLeanDepth) * 8u;
-  constexpr uint32_t kStageBytes = 512u * kLeanDepth;  // per warp and column
+  constexpr int kDepth = UNI ? kLeanDepthUni : kLeanDepth;
+  const uint32_t stage_t = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable) + (uint32_t)(warp * (64 * kDepth) + lane) * 8u;
+  const uint32_t stage_v = stage_t + (uint32_t)kLeanWarps * (64u * kDepth) * 8u;
+  constexpr uint32_t kStageBytes = 512u * kDepth;  // per warp and column
   for (int i = threadIdx.x; i < kRcpTable; i += blockDim.x) rcp_tab[i] = (i > 0) ? 1.0 / (double)i : 0.0;
   __syncthreads();
   LeanRing acc;
@@ -569,12 +599,12 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
   acc.val = rval;
   acc.rcp_tab = rcp_tab;
   acc.init_addresses();
-  acc.flags_sa = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable + kLeanWarps * 128 * kLeanDepth) + (uint32_t)warp * (RING / 32) * 4u;
+  acc.flags_sa = (uint32_t)__cvta_generic_to_shared(rcp_tab + kRcpTable + kLeanWarps * 128 * kDepth) + (uint32_t)warp * (RING / 32) * 4u;
   acc.no_flags = true;
   acc.shape_sa = acc.flags_sa - (uint32_t)warp * (RING / 32) * 4u + (uint32_t)kLeanWarps * (RING / 32) * 4u + (uint32_t)warp * 32u;
   if (lane == 0) sts32(acc.shape_sa + 24u, 0xffffffffu);  // no shape cached yet (a window length never is 2^32 - 1)
   // GROUPED: per-warp "valid throughout" counters of the current group, one per 32-step word (behind everything else)
-  uint32_t* const full_w = reinterpret_cast<uint32_t*>(smem_raw + lean_smem_bytes()) + warp * kLeanFullWords;
+  uint32_t* const full_w = reinterpret_cast<uint32_t*>(smem_raw + lean_smem_bytes(UNI)) + warp * kLeanFullWords;
   if constexpr (GROUPED) {
     for (int i = lane; i < kLeanFullWords; i += 32) full_w[i] = 0u;
     __syncwarp();
@@ -595,7 +625,7 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
     const long long* pt0 = reinterpret_cast<const long long*>(a.ts + r0) + lane;
     const double* pv0 = a.val + r0 + lane;
 #pragma unroll
-    for (int d = 0; d < kLeanDepth - 1; ++d) {  // blocks 0 .. depth-2, one commit group each (empty past the end)
+    for (int d = 0; d < kDepth - 1; ++d) {  // blocks 0 .. depth-2, one commit group each (empty past the end)
       const uint32_t o = 512u * d, r = 64u * d + (uint32_t)lane;
       if (r < cnt) { cp_async8(stage_t + o, pt0 + 64 * d); cp_async8(stage_v + o, pv0 + 64 * d); }
       if (r + 32u < cnt) { cp_async8(stage_t + o + 256u, pt0 + 64 * d + 32); cp_async8(stage_v + o + 256u, pv0 + 64 * d + 32); }
@@ -689,14 +719,17 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
       // in flight into the other half of the staging area (cp.async, one commit group per block)
       const long long* p_t = reinterpret_cast<const long long*>(ts_s) + lane;
       const double* p_v = val_s + lane;
+      // uniform-cadence kernel: the previous block was followed by exactly one uniform pair and nothing else (see
+      // lean_pair's STEADY form)
+      [[maybe_unused]] bool steady = false;
       uint32_t half = 0;                              // staging slot (byte offset) of the block being consumed
-      uint32_t ahead = 512u * (kLeanDepth - 1);       // ... of the block put in flight next
+      uint32_t ahead = 512u * (kDepth - 1);       // ... of the block put in flight next
       while (st.j_cnt < n) {
         const uint32_t j0 = st.j_cnt;  // multiple of 64
         const uint32_t left = n - j0;
         const bool in0 = (uint32_t)lane < left, in1 = (uint32_t)lane + 32u < left;
         {
-          constexpr uint32_t kA = 64u * (kLeanDepth - 1);  // rows ahead
+          constexpr uint32_t kA = 64u * (kDepth - 1);  // rows ahead
           if ((uint32_t)lane + kA < left) { cp_async8(stage_t + ahead, p_t + kA); cp_async8(stage_v + ahead, p_v + kA); }
           if ((uint32_t)lane + kA + 32u < left) { cp_async8(stage_t + ahead + 256u, p_t + kA + 32); cp_async8(stage_v + ahead + 256u, p_v + kA + 32); }
           cp_async_commit();
@@ -704,7 +737,7 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
           p_v += 64;
           ahead = ahead + 512u == kStageBytes ? 0u : ahead + 512u;
         }
-        cp_async_wait<kLeanDepth - 1>();  // everything but the newest depth-1 groups: the block to consume has landed
+        cp_async_wait<kDepth - 1>();  // everything but the newest depth-1 groups: the block to consume has landed
         const long long c_t0 = lds_s64(stage_t + half), c_t1 = lds_s64(stage_t + half + 256u);
         const double c_v0 = LeanRing::lds64(stage_v + half), c_v1 = LeanRing::lds64(stage_v + half + 256u);
         half = half + 512u == kStageBytes ? 0u : half + 512u;
@@ -768,14 +801,62 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
           const double p1 = LeanRing::lds64(pv + 248u);
           bad = bad | (in0 & (c_v0 < p0)) | (in1 & (c_v1 < p1));
         }
+        [[maybe_unused]] bool broken = false;  // (uniform-cadence kernel) a break in the cadence inside this block
         if (__any_sync(0xffffffffu, bad | odd)) {
           if (__any_sync(0xffffffffu, bad)) { defer = 4; break; }
+          if constexpr (UNI) broken = true;
           // the run of equally spaced samples restarts at the newest one, or the series is not one of those
           st.reg_from = __any_sync(0xffffffffu, hard) ? 0xffffffffu : j0 + (left < 64u ? left : 64u) - 1u;
         }
         if constexpr (FLAGS) __syncwarp();  // the bit words are read by every lane below
         st.j_cnt = j0 + (left < 64u ? left : 64u);
         const uint32_t t_new = acc.tm(st.j_cnt - 1u);
+        if constexpr (UNI) {
+          // (the uniform-cadence kernel's copy of the block epilogue below: the steady form in front, and the bookkeeping
+          // that arms it; kept apart so that the general kernel's code is exactly what it was)
+          auto past_the_grid = [&]() {
+            if (t_new < a.rel_max) return false;
+            if (a.filter_nan) {
+              bool nan_left = false;
+              for (uint32_t j = st.j_cnt + (uint32_t)lane; j < n; j += 32u) nan_left = nan_left | isnan(val_s[j]);
+              if (__any_sync(0xffffffffu, nan_left)) defer = 6;
+            }
+            return true;
+          };
+          if (B2P_LEAN_STEADY && steady && !broken && left >= 64u) {
+            lean_pair<FN, FLAGS, GROUPED, UNI, true>(a, st, acc, te, step32, out_p, vw_p, lane, full_p);
+            te += 2u * step32;
+            te31 += 2u * step32;
+            out_p += 64;
+            vw_p += 2 * kVwGroup;
+            full_p += 2;
+            if (past_the_grid()) break;
+            continue;  // (the ring holds what it held one block ago, moved on by 64 samples: room for the next block)
+          }
+          uint32_t n_pairs = 0, n_groups = 0;
+          int last_pair = 0;
+          while (te31 < t_new) {
+            if (B2P_LEAN_PAIR && te31 + step32 < t_new && (last_pair = lean_pair<FN, FLAGS, GROUPED, UNI>(a, st, acc, te, step32, out_p, vw_p, lane, full_p)) != 0) {
+              te += 2u * step32;
+              te31 += 2u * step32;
+              out_p += 64;
+              vw_p += 2 * kVwGroup;
+              full_p += 2;
+              ++n_pairs;
+              continue;
+            }
+            ++n_groups;
+            if ((defer = lean_group<FN, false, FLAGS, GROUPED>(a, st, acc, GROUPED ? st.j_cnt : n, te, 0, 0, out_p, vw_p, lane, full_p))) break;
+            te += step32;
+            te31 += step32;
+            out_p += 32;
+            vw_p += kVwGroup;
+            full_p += 1;
+          }
+          if (defer) break;
+          steady = n_pairs == 1u && n_groups == 0u && last_pair == 2;
+          if (past_the_grid()) break;
+        } else {
         // every group whose last window end is older than the newest sample is final
         while (te31 < t_new) {
           if (B2P_LEAN_PAIR && te31 + step32 < t_new && lean_pair<FN, FLAGS, GROUPED, UNI>(a, st, acc, te, step32, out_p, vw_p, lane, full_p)) {
@@ -807,6 +888,7 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
             if (__any_sync(0xffffffffu, nan_left)) defer = 6;
           }
           break;
+        }
         }
         // nothing seen so far can be inside a window that is still to come (history before the query): restart
         // both edges behind it.  Only before the first non-empty window, where last_range_start is still 0.
@@ -896,7 +978,7 @@ __global__ void __launch_bounds__(kLeanWarps * 32, B2P_LEAN_MIN_BLOCKS) range_le
   cp_async_wait<0>();
 }
 
-__host__ __device__ constexpr size_t lean_grouped_smem_bytes() { return lean_smem_bytes() + (size_t)kLeanWarps * kLeanFullWords * 4; }
+__host__ __device__ constexpr size_t lean_grouped_smem_bytes(bool uni = false) { return lean_smem_bytes(uni) + (size_t)kLeanWarps * kLeanFullWords * 4; }
 
 // Which first-tier variant a call runs (rate / increase / delta, plain): one CTA looks at up to 1024 series spread over
 // the call and counts those whose first (up to) 8 timestamp deltas all equal the eval interval; when at least half of

@@ -96,7 +96,7 @@ int main(int argc, char** argv) {
   constexpr size_t smem = (size_t)kWarpsPerCta * kLeanRing * 16 + kRcpTable * 8 + (size_t)kWarpsPerCta * 2 * 64 * 16 +
                           (size_t)kWarpsPerCta * (kLeanRing / 32) * 4;
 #else
-  constexpr size_t smem = lean_smem_bytes();
+  constexpr size_t smem = lean_smem_bytes(LAB_UNI);
 #endif
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int nb = 0;
