@@ -986,8 +986,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) instant_kernel(const Instan
           if (ts[mid] + a.offset <= te) lo = mid + 1; else hi = mid;
         }
         if (lo > 0) {
-          const uint64_t j = lo - 1;
+          uint64_t j = lo - 1;
           const int64_t t = ts[j] + a.offset;
+          // rows that share the eval timestamp: the reference's cursor stops at the FIRST of them
+          // (instant_manipulate.rs:523-541: `curr == expected` breaks without advancing)
+          if (t == te)
+            while (j > 0 && ts[j - 1] + a.offset == te) --j;
           const bool fresh = (a.lookback > 0) ? (t + a.lookback > te) : (t == te);
           if (fresh) {
             const double v = val[j];

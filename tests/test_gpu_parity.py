@@ -753,6 +753,30 @@ def test_instant_select_matches_oracle_on_irregular_series(ctx):
                      f"instant lookback={lookback} offset={offset}", bit_exact=True)
 
 
+def test_instant_select_takes_the_first_of_rows_that_share_the_eval_timestamp(ctx):
+    """Duplicate timestamps: InstantManipulate's cursor stops at the FIRST row whose timestamp equals the
+    eval timestamp (instant_manipulate.rs:523-541) — also when that row is NaN (stale: no output) and a later duplicate
+    is not; between two timestamps it takes the LAST row at or before (the row in front of the cursor)."""
+    rng = np.random.default_rng(99)
+    ts_l, val_l, offs = [], [], [0]
+    for s in range(40):
+        n = int(rng.integers(1, 300))
+        t = 1_000_000 + np.cumsum(rng.integers(0, 2, n)) * 15_000 + (0 if s % 2 else 7)   # runs of equal timestamps
+        v = rng.normal(size=n) * 10
+        v[rng.random(n) < 0.1] = np.nan
+        ts_l.append(t.astype(np.int64)); val_l.append(v); offs.append(offs[-1] + n)
+    ts, val, offsets = np.concatenate(ts_l), np.concatenate(val_l), np.array(offs, np.uint64)
+    for (start, end, interval, lookback, offset) in ((1_000_000, 3_000_000, 15_000, 300_000, 0),
+                                                     (1_000_000, 3_000_000, 15_000, 0, 0),
+                                                     (1_000_007, 2_500_000, 5_000, 40_000, 0),
+                                                     (940_000, 2_000_000, 15_000, 20_000, -60_000)):
+        out, valid = ctx.instant_select(ts, val, start, end, interval, lookback, offset, offsets=offsets)
+        e_out, e_valid = orc.instant_query(ts, val, offsets, start, end, interval, lookback, offset)
+        T = orc.num_steps(start, end, interval)
+        assert_close(out, e_out, orc.valid_to_bool(valid, T), orc.valid_to_bool(e_valid, T),
+                     f"instant with duplicate timestamps lookback={lookback} offset={offset}", bit_exact=True)
+
+
 def test_device_api_sum_by_partials_and_finalize(ctx):
     """config 3 shape, small: per-shard range_group_sum partials chained into one buffer, then avg finalize."""
     import torch
