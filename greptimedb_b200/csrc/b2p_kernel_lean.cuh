@@ -27,7 +27,12 @@
 //     offsets and first block are fetched while the current one evaluates its last groups;
 //   * the hot shared-memory reads / stores use 32-bit shared-space addresses (ld.shared / st.shared);
 //   * the end trim (range_manipulate.rs:722-728) is applied to the tail groups only — every step
-//     evaluated before the end of the stream is below the trimmed end when range >= interval (host gate).
+//     evaluated before the end of the stream is below the trimmed end when range >= interval (host gate);
+//   * UNI instantiation (rate / increase / delta, plain): where the samples are exactly one eval interval apart the
+//     window edges of 64 steps follow from the previous step's without verification reads, ExtrapolatedRate::calc's
+//     value-independent tail is evaluated once per window shape, and in the steady state (one uniform pair per full
+//     regular block) the block epilogue is skipped altogether — see lean_pair.  cadence_probe_kernel picks the
+//     instantiation per call on the device.
 #pragma once
 #include "b2p_kernels.cuh"
 
@@ -74,7 +79,7 @@ __host__ __device__ constexpr size_t lean_smem_bytes(bool uni = false) {
 
 // The per-warp sample ring of this tier.  Timestamps (uint32 ms since start - range) are stored twice, slot p
 // and slot p + RING, so the edge reads around an index need no wrap handling after set_window(); values are
-// stored once and read through a mask (two reads per step), which keeps four CTAs per SM inside shared memory.
+// stored once and read through a mask (two reads per step).
 template <bool FLAGS>
 struct LeanRingT {
   using time_type = uint32_t;
