@@ -439,6 +439,7 @@ def bench_config2(h: Harness, sampler):
             e2e_step()          # synchronous: returns after the D2H of the result
         torch.cuda.synchronize()
         dt = h.max_over_ranks(time.perf_counter() - t0)
+        h2d_ids = ctx.last_h2d_bytes()   # counted by the library from the copies it issued for one call
         # the same call when the caller (SeriesDivide's boundaries are known to it) hands over series offsets instead of
         # the 4 B/row id column: 16 B/sample over PCIe and no K0
         h.barrier()
@@ -447,11 +448,17 @@ def bench_config2(h: Harness, sampler):
             e2e_step(True)
         torch.cuda.synchronize()
         dt_off = h.max_over_ranks(time.perf_counter() - t0)
+        h2d_off = ctx.last_h2d_bytes()
         res["e2e"] = {"value": Se * N_SAMPLES * h.world * n_e2e / dt, "unit": UNIT,
-                      "h2d_bytes_per_step": Se * N_SAMPLES * 20, "d2h_bytes_per_step": Se * T * 8 + Se * Tw * 4,
+                      "h2d_bytes_per_step": h2d_ids, "d2h_bytes_per_step": Se * T * 8 + Se * Tw * 4,
+                      "host_columns_bytes_per_step": Se * N_SAMPLES * 20,
+                      "h2d_note": ("the call takes the i64 timestamp, f64 value and u32 id columns in pinned host memory; it scans "
+                                   "them on the host (worker threads, ahead of the copies) and sends chunks of equally spaced "
+                                   "series as values + (offsets, first timestamp, cadence) per series, every other chunk as it "
+                                   "is (B2P_HOST_TS_SCAN=0: always as it is)"),
                       "series_per_step": Se, "steps": n_e2e, "pinned_numa_node": numa_node,
                       "with_series_offsets_instead_of_ids": {"value": Se * N_SAMPLES * h.world * n_e2e / dt_off,
-                                                             "h2d_bytes_per_step": Se * N_SAMPLES * 16 + (Se + 1) * 8}}
+                                                             "h2d_bytes_per_step": h2d_off}}
         del h_ts, h_val, h_sid, h_out, h_valid, h_off
     del ts, val, sid, offsets, out, valid
     h.free()

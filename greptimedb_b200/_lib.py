@@ -14,14 +14,14 @@ LIB_PATH = os.environ.get("B2P_LIB_PATH") or os.path.join(_HERE, "libb200promql.
 # every symbol include/b200promql.h declares (tests/test_abi.py checks the .so exports them all)
 EXPORTED_SYMBOLS = [
     "b2p_create", "b2p_destroy", "b2p_last_error", "b2p_version", "b2p_set_stream", "b2p_use_own_stream", "b2p_sync", "b2p_num_steps",
-    "b2p_last_slow_series", "b2p_last_warp_tier_series", "b2p_last_kernel_ms", "b2p_launch_count",
+    "b2p_last_slow_series", "b2p_last_h2d_bytes", "b2p_last_warp_tier_series", "b2p_last_kernel_ms", "b2p_launch_count",
     "b2p_series_offsets_dev", "b2p_range_eval_dev", "b2p_range_udf_dev", "b2p_instant_select_dev",
     "b2p_group_aggregate_dev", "b2p_range_group_sum_dev", "b2p_group_finalize_dev", "b2p_histogram_quantile_dev",
     "b2p_group_index_create_dev", "b2p_group_index_destroy", "b2p_group_aggregate_indexed_dev",
     "b2p_range_group_sum_indexed_dev", "b2p_range_group_sum_fused", "b2p_group_aggregate_partial_dev",
     "b2p_comm_unique_id", "b2p_comm_init", "b2p_comm_destroy", "b2p_allreduce_partials_dev",
     "b2p_range_group_sum_allreduce_dev", "b2p_allreduce_columns_dev", "b2p_histogram_fold_dev", "b2p_range_histogram_fold",
-    "b2p_column_reduce_dev", "b2p_range_eval", "b2p_range_udf", "b2p_instant_select", "b2p_group_aggregate",
+    "b2p_column_reduce_dev", "b2p_host_scan_series", "b2p_range_eval", "b2p_range_udf", "b2p_instant_select", "b2p_group_aggregate",
     "b2p_histogram_quantile", "b2p_synth_fill_dev",
     "b2p_plan_range_create", "b2p_plan_set_instant", "b2p_plan_set_histogram_quantile", "b2p_plan_push_batch", "b2p_plan_execute", "b2p_plan_num_series", "b2p_plan_destroy",
     "b2p_plan_last_error",
@@ -64,6 +64,7 @@ def load() -> C.CDLL:
         "b2p_sync": (C.c_int, [vp]),
         "b2p_num_steps": (i64, [i64, i64, i64]),
         "b2p_last_slow_series": (i64, [vp]),
+        "b2p_last_h2d_bytes": (i64, [vp]),
         "b2p_last_warp_tier_series": (i64, [vp]),
         "b2p_last_kernel_ms": (dbl, [vp, C.c_int]),
         "b2p_launch_count": (i64, [vp]),
@@ -90,6 +91,7 @@ def load() -> C.CDLL:
         "b2p_range_histogram_fold": (C.c_int, [vp, P, vp, vp, vp, vp, u64, u32, dbl, vp, vp, vp, u32, vp, vp]),
         "b2p_histogram_quantile_dev": (C.c_int, [vp, dbl, vp, u32, vp, vp, u32, u64, vp, vp]),
         "b2p_column_reduce_dev": (C.c_int, [vp, vp, u32, u64, vp, vp]),
+        "b2p_host_scan_series": (C.c_int, [vp, vp, vp, u64, u32, u32, vp, vp, vp, vp]),
         "b2p_range_eval": (C.c_int, [vp, P, vp, vp, vp, vp, u64, u32, vp, vp, vp]),
         "b2p_range_udf": (C.c_int, [vp, i32, vp, vp, u64, vp, vp, u64, i64, dbl, dbl, vp, vp]),
         "b2p_instant_select": (C.c_int, [vp, i64, i64, i64, i64, i64, vp, vp, vp, vp, u64, u32, vp, vp]),

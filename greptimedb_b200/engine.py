@@ -113,6 +113,9 @@ class Context:
     def last_slow_series(self) -> int:
         return int(self._L.b2p_last_slow_series(self._h))
 
+    def last_h2d_bytes(self) -> int:
+        return int(self._L.b2p_last_h2d_bytes(self._h))
+
     def last_warp_tier_series(self) -> int:
         return int(self._L.b2p_last_warp_tier_series(self._h))
 

@@ -133,6 +133,9 @@ B2P_API int b2p_sync(b2p_ctx* ctx);
 B2P_API int64_t b2p_num_steps(int64_t start, int64_t end, int64_t interval);
 /* Series the last range/instant call routed to the exact slow path (diagnostic; after b2p_sync). */
 B2P_API int64_t b2p_last_slow_series(b2p_ctx* ctx);
+/* bytes the last b2p_range_eval (host-pointer call) copied host -> device: fewer than 20 B/row when chunks of equally
+ * spaced series went over as (offsets, first timestamp, cadence) descriptors instead of their timestamp / id columns */
+B2P_API int64_t b2p_last_h2d_bytes(b2p_ctx* ctx);
 /* Series the thread-per-series tier handed to the warp-per-series kernel in the last call (diagnostic). */
 B2P_API int64_t b2p_last_warp_tier_series(b2p_ctx* ctx);
 /* CUDA-event time (ms) of the kernels of the last *_dev / host call, by stage index:
@@ -238,6 +241,18 @@ B2P_API int b2p_histogram_fold_dev(b2p_ctx* ctx, double phi, const uint32_t* his
  * skipped (SeriesNormalize filter).  out_sum[n_cols], out_cnt[n_cols] accumulate. */
 B2P_API int b2p_column_reduce_dev(b2p_ctx* ctx, const double* const* cols, uint32_t n_cols, uint64_t n_rows,
                           double* out_sum, uint64_t* out_cnt);
+
+/* ---- host-side helper (no device work) -------------------------------------------------------- */
+/* SeriesDivide (series_divide.rs:540-670) plus a cadence scan of one sorted batch on the HOST: series boundaries from
+ * the id column `sid` (ids sid_base .. sid_base + n_series - 1, non-decreasing), or copied from `offsets_in`
+ * (n_series + 1) when sid is NULL, into offsets_out (n_series + 1); and per series t0 = its first timestamp and
+ * cadence = ts[1] - ts[0] (0 for series of fewer than two rows).  *all_regular = 1 iff ts[i] == t0 + i * cadence holds
+ * for every row of every series — then the timestamp column is fully described by (offsets, t0, cadence), which is what
+ * b2p_range_eval sends over PCIe instead of it (8 B/row less; the device rebuilds the column).  Any of t0 / cadence /
+ * all_regular may be NULL.  B2P_E_UNSORTED when the ids are not non-decreasing or out of range. */
+B2P_API int b2p_host_scan_series(const int64_t* ts, const uint32_t* sid, const uint64_t* offsets_in, uint64_t n_rows,
+                         uint32_t n_series, uint32_t sid_base, uint64_t* offsets_out, int64_t* t0, int64_t* cadence,
+                         int32_t* all_regular);
 
 /* ---- host-pointer API (synchronous; H2D + kernels + D2H inside) ----------------------------- */
 /* sid may be NULL when offsets_host (n_series+1) is given instead. out_ts (may be NULL) receives

@@ -132,6 +132,7 @@ extern "C" {
     pub fn b2p_sync(ctx: *mut b2p_ctx) -> c_int;
     pub fn b2p_num_steps(start: i64, end: i64, interval: i64) -> i64;
     pub fn b2p_last_slow_series(ctx: *mut b2p_ctx) -> i64;
+    pub fn b2p_last_h2d_bytes(ctx: *mut b2p_ctx) -> i64;
     pub fn b2p_last_warp_tier_series(ctx: *mut b2p_ctx) -> i64;
     pub fn b2p_last_kernel_ms(ctx: *mut b2p_ctx, stage: c_int) -> f64;
     pub fn b2p_launch_count(ctx: *mut b2p_ctx) -> i64;
@@ -199,6 +200,12 @@ extern "C" {
     ) -> c_int;
     pub fn b2p_column_reduce_dev(
         ctx: *mut b2p_ctx, cols: *const *const f64, n_cols: u32, n_rows: u64, out_sum: *mut f64, out_cnt: *mut u64,
+    ) -> c_int;
+
+    // ---- host-side helper (no device work): SeriesDivide + cadence scan of one sorted batch ---------------------------
+    pub fn b2p_host_scan_series(
+        ts: *const i64, sid: *const u32, offsets_in: *const u64, n_rows: u64, n_series: u32, sid_base: u32,
+        offsets_out: *mut u64, t0: *mut i64, cadence: *mut i64, all_regular: *mut i32,
     ) -> c_int;
 
     // ---- host-pointer API (synchronous) ------------------------------------------------------------------------------

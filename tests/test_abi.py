@@ -75,3 +75,40 @@ def test_rust_ffi_declares_every_header_symbol():
     src = open(os.path.join(ROOT, "rust-shim", "src", "ffi.rs")).read()
     declared = set(re.findall(r"pub fn (b2p_[a-z0-9_]+)\s*\(", src))
     assert sorted(declared) == _declared_symbols()
+
+
+def test_host_scan_series_divides_and_describes_regular_series():
+    """b2p_host_scan_series (no device work): SeriesDivide's boundaries on the host plus, per series, (first timestamp,
+    cadence) and whether ts[i] == t0 + i * cadence for every row — what b2p_range_eval sends instead of the timestamp
+    and id columns when it holds."""
+    import ctypes as C
+    import numpy as np
+    from greptimedb_b200 import _lib
+    L = _lib.load()
+
+    def scan(ts, sid, offs, n_series, base=0):
+        ts = np.ascontiguousarray(ts, np.int64)
+        out = np.zeros(n_series + 1, np.uint64)
+        t0 = np.zeros(n_series, np.int64)
+        cad = np.zeros(n_series, np.int64)
+        reg = C.c_int32(-1)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        sid = None if sid is None else np.ascontiguousarray(sid, np.uint32)
+        offs = None if offs is None else np.ascontiguousarray(offs, np.uint64)
+        rc = L.b2p_host_scan_series(p(ts), p(sid), p(offs), ts.size, n_series, base, p(out), p(t0), p(cad), C.addressof(reg))
+        return rc, out, t0, cad, reg.value
+
+    # series 5 (3 rows), 6 (empty), 7 (1 row), 8 (4 rows, step 0: duplicate timestamps), 9 (2 rows); ids start at 5
+    ts = np.array([100, 115, 130, 7, 50, 50, 50, 50, -3, 9], np.int64)
+    sid = np.array([5, 5, 5, 7, 8, 8, 8, 8, 9, 9], np.uint32)
+    rc, off, t0, cad, reg = scan(ts, sid, None, 5, base=5)
+    assert rc == 0 and off.tolist() == [0, 3, 3, 4, 8, 10]
+    assert t0.tolist() == [100, 0, 7, 50, -3] and cad.tolist() == [15, 0, 0, 0, 12] and reg == 1
+    # the same through offsets (rebased to the batch), one row off the cadence
+    ts2 = ts.copy(); ts2[2] += 1
+    rc, off2, _, cad2, reg2 = scan(ts2, None, np.array([40, 43, 43, 44, 48, 50], np.uint64), 5)
+    assert rc == 0 and off2.tolist() == off.tolist() and cad2.tolist() == cad.tolist() and reg2 == 0
+    # ids out of order / out of range are errors (B2P_E_UNSORTED = -3)
+    assert scan(ts, np.array([5, 5, 6, 5, 8, 8, 8, 8, 9, 9]), None, 5, base=5)[0] == -3
+    assert scan(ts, sid, None, 4, base=5)[0] == -3
+    assert scan(ts, sid, None, 5, base=6)[0] == -3

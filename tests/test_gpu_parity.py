@@ -724,6 +724,54 @@ def test_pipelined_host_path_matches_oracle(ctx):
     assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size), "pipelined slow path")
 
 
+def test_pipelined_host_path_sends_descriptors_for_equally_spaced_chunks(ctx):
+    """b2p_range_eval scans every chunk on the host; where all series of a chunk are equally spaced it sends (offsets,
+    first timestamp, cadence) instead of the timestamp and id columns and the device rebuilds the column
+    (ts_expand_kernel).  Regular chunks, a chunk with one timestamp off the cadence (ordinary route) and ragged series
+    lengths, through the id column and through offsets; B2P_HOST_TS_SCAN=0 gives the same bits."""
+    import os
+    from greptimedb_b200 import Context, make_params
+    T0, SC = 1_700_000_000_000, 15_000
+    rng = np.random.default_rng(21)
+    S = 9000
+    lens = rng.integers(900, 1001, S)
+    lens[::97] = 0
+    lens[5::211] = 1
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    n = int(offsets[-1])
+    sid = np.repeat(np.arange(S, dtype=np.uint32), lens)
+    idx = np.arange(n) - np.repeat(offsets[:-1].astype(np.int64), lens)
+    phase = np.repeat(rng.integers(0, 4, S) * 7, lens)          # a few start phases; cadence = scrape for all
+    ts = (T0 + phase + idx * SC).astype(np.int64)
+    val = np.cumsum(rng.random(n)) + 1.0
+    val[::4099] = np.nan
+    ts_broken = ts.copy()
+    ts_broken[int(offsets[5000]) + 17] += 3                      # one row off the cadence in the second chunk
+    os.environ["B2P_HOST_TS_SCAN"] = "0"
+    try:
+        plain = Context(0)
+    finally:
+        del os.environ["B2P_HOST_TS_SCAN"]
+    try:
+        for tsx, tag in ((ts, "regular"), (ts_broken, "one chunk irregular")):
+            for fn, interval in (("rate", SC), ("avg_over_time", 60_000)):
+                p = make_params(fn, T0, T0 + 999 * SC, interval, 300_000)
+                op = orc.make_params(fn, T0, T0 + 999 * SC, interval, 300_000)
+                e_out, e_valid = orc.range_query(op, tsx, val, None, offsets, threads=8)
+                ref = None
+                for c, use_sid in ((ctx, True), (ctx, False), (plain, True)):
+                    out, valid, ets = c.range_eval_n(p, tsx, val, sid if use_sid else None, None if use_sid else offsets, S)
+                    assert_close(out, e_out, orc.valid_to_bool(valid, ets.size), orc.valid_to_bool(e_valid, ets.size),
+                                 f"host scan {tag} {fn} sid={use_sid}")
+                    if ref is None:
+                        ref = (out, valid)
+                    else:
+                        vb = orc.valid_to_bool(valid, ets.size)
+                        assert (valid == ref[1]).all() and (out.view(np.uint64)[vb] == ref[0].view(np.uint64)[vb]).all()
+    finally:
+        plain.close()
+
+
 def test_group_aggregate_matches_oracle(ctx):
     rng = np.random.default_rng(3)
     S, T, G = 700, 77, 13
