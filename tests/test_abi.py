@@ -112,3 +112,21 @@ def test_host_scan_series_divides_and_describes_regular_series():
     assert scan(ts, np.array([5, 5, 6, 5, 8, 8, 8, 8, 9, 9]), None, 5, base=5)[0] == -3
     assert scan(ts, sid, None, 4, base=5)[0] == -3
     assert scan(ts, sid, None, 5, base=6)[0] == -3
+
+
+def test_host_scan_series_on_the_reference_series_divide_fixture():
+    """series_divide.rs:668-905 through the library's host-side SeriesDivide: the same 7 boundaries."""
+    import ctypes as C
+    import numpy as np
+    from greptimedb_b200 import _lib
+    from tests.helpers import load_unit
+    from tests.test_oracle_golden import _series_divide_ids
+    g = load_unit()["series_divide"]
+    _, ids = _series_divide_ids(g)
+    ts = np.array([t for b in g["batches"] for t in b["ts"]], np.int64)
+    out = np.zeros(8, np.uint64)
+    reg = C.c_int32(-1)
+    L = _lib.load()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.b2p_host_scan_series(p(ts), p(ids), None, ts.size, 7, 0, p(out), None, None, C.addressof(reg)) == 0
+    assert out.tolist() == g["expected_offsets"] and reg.value == 1   # (its timestamps are 1 s apart throughout)

@@ -64,6 +64,24 @@ def test_nan_series_and_null_filter_rows(ctx):
     assert ex.num_series() == 5
 
 
+def test_series_divide_reference_fixture_through_the_plan(ctx):
+    """series_divide.rs:668-905: three RecordBatches, two Utf8 tag columns (multi-byte values), one series spanning all
+    three batches -> 7 series with the reference's row counts (count_over_time over everything, one eval step)."""
+    from greptimedb_b200.plan import PromRangeExec
+    from tests.helpers import load_unit
+    g = load_unit()["series_divide"]
+    ex = PromRangeExec(ctx, "prom_count_over_time", 23_000, 23_000, 1_000, 60_000, "ts", "val", g["tag_columns"])
+    for b in g["batches"]:
+        n = len(b["ts"])
+        ex.push(pa.record_batch([pa.array(b["ts"], pa.timestamp("ms")), pa.array([1.0] * n, pa.float64()),
+                                 pa.array(b["host"], pa.string()), pa.array(b["path"], pa.string())],
+                                names=["ts", "val", "host", "path"]))
+    out = ex.execute()
+    assert ex.num_series() == 7
+    got = list(zip(out.column("host").to_pylist(), out.column("path").to_pylist(), out.column(1).to_pylist()))
+    assert got == [(e["host"], e["path"], float(e["rows"])) for e in g["expected_series"]]
+
+
 def test_sum_by_plan_matches_oracle_and_is_sorted(ctx):
     """sum by (pod)(rate(http_requests_total[5m])) on synthetic series: rows sorted by (label, ts)."""
     from greptimedb_b200.plan import PromRangeExec

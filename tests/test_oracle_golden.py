@@ -136,6 +136,28 @@ def test_series_divide():
     assert orc.series_divide([1]).tolist() == [0, 1]
 
 
+def _series_divide_ids(g):
+    """Dense ids by key change over the concatenated batches (what the plan layer hands K0)."""
+    keys = [tuple(b[t][i] for t in g["tag_columns"]) for b in g["batches"] for i in range(len(b["ts"]))]
+    ids, cur = [], -1
+    for i, k in enumerate(keys):
+        if i == 0 or k != keys[i - 1]:
+            cur += 1
+        ids.append(cur)
+    return keys, np.array(ids, np.uint32)
+
+
+def test_series_divide_reference_table():
+    """The reference's own SeriesDivide fixture (series_divide.rs:668-905: three input batches, a series that spans all
+    of them, multi-byte tag values): 7 series with the row counts of `per_batch_data`."""
+    g = UNIT["series_divide"]
+    keys, ids = _series_divide_ids(g)
+    assert orc.series_divide(ids).tolist() == g["expected_offsets"]
+    firsts = [keys[o] for o in g["expected_offsets"][:-1]]
+    assert firsts == [(e["host"], e["path"]) for e in g["expected_series"]]
+    assert np.diff(g["expected_offsets"]).tolist() == [e["rows"] for e in g["expected_series"]]
+
+
 def _resolve_series(case):
     return case["series"] if "series" in case else SQL["series_sets"][case["series_ref"]]
 
