@@ -376,3 +376,39 @@ def test_le_label_parse_follows_rust():
         assert orc.parse_f64_rust(s) == float("inf"), s
     for s in lp["nan"]:
         assert np.isnan(orc.parse_f64_rust(s)), repr(s)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tql/range.result: sum(rate()) / sum by (..)(rate()) on the reference's own table — the BASELINE config-3 query shape
+# ---------------------------------------------------------------------------------------------------------------
+import json as _json
+import os as _os
+
+SUM_RATE = _json.load(open(_os.path.join(_os.path.dirname(__file__), "golden", "reference_sum_rate_vectors.json")))
+
+
+@pytest.mark.parametrize("case", SUM_RATE["cases"], ids=lambda c: c["name"])
+def test_sum_rate_reference_tables(case):
+    """rate() per series through the oracle's range path, then the by-label SUM (DataFusion's accumulator: plain f64 +=
+    in series order), label matchers applied the way the scan would; every printed value of range.result reproduced to
+    the last digit (they are the shortest round-trip decimals of the f64 results)."""
+    keep = [s for s in SUM_RATE["series"] if all(s[k] == v for k, v in case["filter"].items())]
+    if not keep:
+        assert case["expected"] == []
+        return
+    ts = np.concatenate([np.array(s["ts"], np.int64) for s in keep])
+    val = np.concatenate([np.array(s["val"], np.float64) for s in keep])
+    offsets = np.concatenate([[0], np.cumsum([len(s["ts"]) for s in keep])]).astype(np.uint64)
+    p = orc.make_params("rate", case["start"], case["end"], case["interval"], case["range"])
+    out, valid = orc.range_query(p, ts, val, None, offsets, mode="faithful")
+    keys = sorted({tuple(s[t] for t in case["by"]) for s in keep})
+    gid = np.array([keys.index(tuple(s[t] for t in case["by"])) for s in keep], np.uint32)
+    gsum, gcnt = orc.group_aggregate("sum", out, valid, gid, len(keys))
+    T = orc.num_steps(case["start"], case["end"], case["interval"])
+    got = []
+    for g, key in enumerate(keys):
+        for k in range(T):
+            if gcnt[g, k]:
+                got.append([dict(zip(case["by"], key)), case["start"] + k * case["interval"],
+                            float(gsum[g, k]) * case.get("scale", 1.0)])
+    assert got == case["expected"]
