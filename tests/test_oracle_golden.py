@@ -412,3 +412,21 @@ def test_sum_rate_reference_tables(case):
                 got.append([dict(zip(case["by"], key)), case["start"] + k * case["interval"],
                             float(gsum[g, k]) * case.get("scale", 1.0)])
     assert got == case["expected"]
+
+
+@pytest.mark.parametrize("case", SQL.get("function_cases", []), ids=lambda c: c["name"])
+def test_sqlness_function_cases(case):
+    """promql/functions.result (predict_linear, double_exponential_smoothing / holt_winters, quantile_over_time with scalar
+    expressions as parameters) and the irate table of tql/operator.result (eval grid on half seconds, issue 5880): the
+    printed rows, value for value."""
+    names, ts, val, sid, offsets = pack_series(case["series"])
+    p = orc.make_params(case["fn"], case["start"], case["end"], case["interval"], case["range"],
+                        param0=case.get("param0", 0.0), param1=case.get("param1", 0.0))
+    out, valid = orc.range_query(p, ts, val, sid, offsets, mode="faithful")
+    T = orc.num_steps(case["start"], case["end"], case["interval"])
+    vb = orc.valid_to_bool(valid, T)
+    got = {(names[s], case["start"] + k * case["interval"]): float(out[s, k]) for s in range(len(names)) for k in range(T) if vb[s, k]}
+    exp = {(n, t): fnum(v) for n, t, v in case["expected"]}
+    assert set(got) == set(exp), (case["name"], sorted(got))
+    for key, e in exp.items():
+        assert got[key] == e, (case["name"], key, got[key], e)
