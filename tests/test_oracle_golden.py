@@ -195,6 +195,12 @@ def test_sqlness_instant_cases(case):
     assert got == exp
 
 
+@pytest.mark.parametrize("case", SQL.get("instant_offset_direction_cases", []), ids=lambda c: c["name"])
+def test_sqlness_instant_offset_direction(case):
+    """promql/offset_direction.result: a positive offset reads the past, a negative one the future."""
+    test_sqlness_instant_cases(case)
+
+
 @pytest.mark.parametrize("case", SQL["histogram_cases"], ids=lambda c: c["name"])
 def test_sqlness_histogram_cases(case):
     B = len(case["le"])
@@ -430,3 +436,30 @@ def test_sqlness_function_cases(case):
     assert set(got) == set(exp), (case["name"], sorted(got))
     for key, e in exp.items():
         assert got[key] == e, (case["name"], key, got[key], e)
+
+
+def test_histogram_quantile_over_sum_by_le_across_partitions():
+    """promql/histogram_multi_partition.result: histogram_quantile(0.5, sum by (le)(histogram_gap_bucket)) over a table
+    partitioned by `shard` — instant selector per (shard, le) series, SUM by le merged across the two partitions
+    (__sum_state / __sum_merge, commutativity.rs:85-113: partial sums and counts add), then the fold: 0.5 and
+    0.5833333333333334.  The per-partition partials added together equal the single-pass aggregate."""
+    rows = [(0, "0.5", "a", 1), (0, "1", "a", 2), (0, "+Inf", "a", 2), (0, "0.5", "z", 2), (0, "1", "z", 4), (0, "+Inf", "z", 4),
+            (10000, "0.5", "a", 1), (10000, "1", "a", 2), (10000, "+Inf", "a", 2), (10000, "0.5", "z", 1), (10000, "1", "z", 3),
+            (10000, "+Inf", "z", 3)]
+    keys = sorted({(sh, le) for _, le, sh, _ in rows})                      # series = (shard, le), SeriesDivide order
+    les = sorted({le for _, le, _, _ in rows}, key=lambda s: orc.parse_f64_rust(s))
+    ts = np.array([t for k in keys for t, le, sh, v in rows if (sh, le) == k], np.int64)
+    val = np.array([float(v) for k in keys for t, le, sh, v in rows if (sh, le) == k])
+    offsets = np.arange(len(keys) + 1, dtype=np.uint64) * 2
+    out, valid = orc.instant_query(ts, val, offsets, 0, 10000, 10000, 300000, 0)
+    gid = np.array([les.index(le) for _, le in keys], np.uint32)
+    gsum, gcnt = orc.group_aggregate("sum", out, valid, gid, len(les))
+    # the two partitions (shard < 'n', shard >= 'n') aggregated on their own, then merged
+    parts = []
+    for pick in (lambda sh: sh < "n", lambda sh: sh >= "n"):
+        idx = [i for i, (sh, _) in enumerate(keys) if pick(sh)]
+        parts.append(orc.group_aggregate("sum", out[idx], valid[idx], gid[idx], len(les)))
+    assert ((parts[0][0] + parts[1][0]) == gsum).all() and ((parts[0][1] + parts[1][1]) == gcnt).all()
+    bounds = [orc.parse_f64_rust(le) for le in les]
+    got = [orc.histogram_evaluate_row(0.5, bounds, gsum[:, k])[0] for k in range(2)]
+    assert got == [0.5, 0.5833333333333334]
