@@ -463,3 +463,20 @@ def test_histogram_quantile_over_sum_by_le_across_partitions():
     bounds = [orc.parse_f64_rust(le) for le in les]
     got = [orc.histogram_evaluate_row(0.5, bounds, gsum[:, k])[0] for k in range(2)]
     assert got == [0.5, 0.5833333333333334]
+
+
+def test_tsid_regression_tables():
+    """promql/tsid_histogram_quantile_regression.result: avg_over_time(m[5s]) at a 5 s step over samples at 0 / 5 / 10 s
+    (each window (t - 5 s, t] holds exactly the sample at t: 1, 3, 5), and histogram_quantile(0.5, buckets 1 / 2 / +Inf)
+    through the instant selector + fold: 1.5 at every step."""
+    ts = np.array([0, 5000, 10000], np.int64)
+    p = orc.make_params("avg_over_time", 0, 10000, 5000, 5000)
+    out, valid = orc.range_query(p, ts, np.array([1.0, 3.0, 5.0]), None, np.array([0, 3], np.uint64), mode="faithful")
+    assert orc.valid_to_bool(valid, 3).all() and out[0].tolist() == [1.0, 3.0, 5.0]
+    # buckets '1', '2', '+Inf' of job1: counters 1,2,3 / 2,4,6 / 3,6,9
+    bts = np.tile(ts, 3)
+    bval = np.array([1, 2, 3, 2, 4, 6, 3, 6, 9], np.float64)
+    sel, sv = orc.instant_query(bts, bval, np.array([0, 3, 6, 9], np.uint64), 0, 10000, 5000, 300000, 0)
+    assert orc.valid_to_bool(sv, 3).all()
+    bounds = [orc.parse_f64_rust(s) for s in ("1", "2", "+Inf")]
+    assert [orc.histogram_evaluate_row(0.5, bounds, sel[:, k])[0] for k in range(3)] == [1.5, 1.5, 1.5]
