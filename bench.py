@@ -752,6 +752,9 @@ def main():
     args = ap.parse_args()
     global JITTER_MS
     JITTER_MS = args.jitter_ms
+    # NCCL's banner ("NCCL version ...", printed to stdout at NCCL_DEBUG=VERSION) would precede the one JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     if args.impl == "reference":
         run_reference(args)
     else:
